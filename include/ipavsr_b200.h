@@ -1,0 +1,205 @@
+/*
+ * ipavsr_b200 — C-ABI of the B200-native (sm_100a) AdeNet/DeltaNet hot path.
+ *
+ * The reference (lzuwei/ip-avsr) has no FFI: every op below is Theano/Lasagne graph code that Theano JIT-compiles
+ * (SURVEY.md §2.1).  Each entry point therefore cites the reference *function* whose arithmetic it replaces
+ * (file:line under the reference tree) instead of a binding it would be bound from; INTEGRATION.md shows the
+ * ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless it says "host".
+ *   - matrices are row-major float32 with an explicit leading dimension (`ld*`, in floats).
+ *   - sequences (N utterances, T padded frames, F features) are matrices of N*T rows, row = n*T + t.
+ *   - masks are uint8 (N,T), a prefix of ones per utterance (reference utils/datagen.py:131,141-142).
+ *   - every call is asynchronous on the caller's `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     returns 0 on success or a negative code; `ipavsr_last_error()` gives the message (thread-local).
+ *   - nothing here falls back to the CPU.
+ */
+#ifndef IPAVSR_B200_H
+#define IPAVSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPAVSR_OK 0
+#define IPAVSR_ERR_ARG -1
+#define IPAVSR_ERR_CUDA -2
+#define IPAVSR_ERR_UNSUPPORTED -3
+
+/* nonlinearity codes (reference custom/nonlinearities.py:4-16 -> lasagne.nonlinearities) */
+#define IPAVSR_ACT_LINEAR 0
+#define IPAVSR_ACT_SIGMOID 1
+#define IPAVSR_ACT_RECTIFY 2
+#define IPAVSR_ACT_TANH 3
+#define IPAVSR_ACT_LEAKY 4
+#define IPAVSR_ACT_VERY_LEAKY 5
+#define IPAVSR_ACT_SOFTPLUS 6
+#define IPAVSR_ACT_ELU 7
+
+/* GEMM arithmetic modes */
+#define IPAVSR_GEMM_FP32 0      /* CUDA-core FFMA, fp32 throughout                                   */
+#define IPAVSR_GEMM_TF32X3 1    /* tcgen05 kind::tf32, 3-term error-compensated split (fp32 parity)  */
+#define IPAVSR_GEMM_TF32 2      /* tcgen05 kind::tf32, single pass (states its own tolerance)        */
+#define IPAVSR_GEMM_BF16X3 3    /* reserved */
+
+/* optimiser kinds (reference custom/updates.py:35-99; lasagne.updates adam/adadelta/sgd/momentum) */
+#define IPAVSR_OPT_ADAM 0
+#define IPAVSR_OPT_ADADELTA 1
+#define IPAVSR_OPT_SGD 2
+#define IPAVSR_OPT_MOMENTUM 3
+#define IPAVSR_OPT_NESTEROV 4
+
+const char* ipavsr_last_error(void);
+int ipavsr_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches counter) */
+uint64_t ipavsr_launch_count(void);
+/* device properties the host side sizes grids with; returns 0 or a negative code */
+int ipavsr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
+
+/* ---- a1: DenseLayer  y = act(x W + b)  (modelzoo/pretrained_encoder.py:4-9; lasagne DenseLayer) ----------
+ * C[M,N] = act( op(A)[M,K] * op(B)[K,N] (+ C if accumulate) + bias[N] ).
+ * transA=0: A is [M,K] (lda>=K);  transA=1: A is stored [K,M] (lda>=M).  transB likewise ([K,N] / [N,K]).
+ * Used for the encoder stack, the hoisted LSTM input projections, the softmax head and every dgrad/wgrad.
+ * `mode` is one of IPAVSR_GEMM_*; tensor-core modes need `workspace` of ipavsr_gemm_workspace_bytes(). */
+int ipavsr_gemm(int mode, int transA, int transB, int M, int N, int K,
+                const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                const float* bias, int act, int accumulate,
+                void* workspace, uint64_t workspace_bytes, void* stream);
+uint64_t ipavsr_gemm_workspace_bytes(int mode, int transA, int transB, int M, int N, int K);
+
+/* dZ = dY * act'(Y)  and  db[N] (+)= column sums of dZ   (backward of DenseLayer's nonlinearity and bias).
+ * dZ may alias dY.  db may be NULL. */
+int ipavsr_dense_bwd_prep(const float* dY, int lddy, const float* Y, int ldy, float* dZ, int lddz,
+                          float* db, int M, int N, int act, int accumulate_db, void* stream);
+/* out[N] (+)= column sums of X[M,N] */
+int ipavsr_colsum(const float* X, int ldx, float* out, int M, int N, int accumulate, void* stream);
+
+/* ---- a2: DeltaLayer  (custom/layers.py:105-121 -> utils/signal.py:59-80) -------------------------------
+ * x (N*T, F; ldx) -> y (N*T, 3F; ldy) = [x | delta | accel], window half-width theta, edge-replicated,
+ * mask-agnostic.  exact=1 reproduces the reference's float64 intermediates with a float32 round per theta. */
+int ipavsr_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, int T, int F, int theta, int exact,
+                     void* stream);
+/* gx (N*T, F) (+)= gy[:, :F] + D^T (gy[:, F:2F] + D^T gy[:, 2F:]) */
+int ipavsr_delta_bwd(const float* gy, int ldgy, float* gx, int ldgx, int N, int T, int F, int theta,
+                     int accumulate, void* stream);
+
+/* ---- a3: Lasagne LSTMLayer recurrence (custom/layers.py:10-80) ---------------------
+ * Device parameter layout (gate-interleaved): column j = 4*u + g of the stacked (.,4H) matrices holds unit u,
+ * gate g in {0:ingate, 1:forgetgate, 2:cell, 3:outgate}.
+ *   xw     (N*T, 4H)  precomputed x W_in + b (one ipavsr_gemm over all frames), interleaved columns
+ *   w_hid  (H, 4H)    interleaved columns
+ *   peep   (3, H) rows = W_cell_to_{ingate,forgetgate,outgate}, or NULL (no peepholes)
+ *   out    (N*T, H; ldh) hidden state per frame, aligned with the input frame (re-reversed if `backwards`);
+ *          `ldh` is the leading dimension of out, hprev and dout (cell is dense, ld = H)
+ * Training saves (may all be NULL for inference): gates (N*T,4H) post-nonlinearity, cell (N*T,H) masked cell
+ * state, hprev (N*T,H) the hidden state that entered each step.
+ * impl: 0 = persistent cluster kernel (W_hid resident in shared memory across a thread-block cluster),
+ *       1 = one launch per time step (simple form, kept as a cross-check). */
+int ipavsr_lstm_fwd(const float* xw, const float* w_hid, const float* peep, const float* cell_init,
+                    const float* hid_init, const uint8_t* mask, float* out, float* gates, float* cell,
+                    float* hprev, int N, int T, int H, int ldh, int backwards, int impl,
+                    void* workspace, uint64_t workspace_bytes, void* stream);
+/* dout (N*T,H) -> dgates (N*T,4H) = clipped gradient w.r.t. the pre-peephole gate pre-activations (this is
+ * d(xw); W_in/W_hid/b/input gradients follow from it with ipavsr_gemm / ipavsr_colsum), dpeep (3,H) (+)=,
+ * dcell_init (H) (+)=, dhid_init (H) (+)=.  clip<=0 disables the gradient clip. */
+int ipavsr_lstm_bwd(const float* dout, const float* w_hid, const float* peep, const float* cell_init,
+                    const uint8_t* mask, const float* gates, const float* cell,
+                    float* dgates, float* dpeep, float* dcell_init, float* dhid_init,
+                    int N, int T, int H, int ldh, int backwards, float clip, int accumulate, int impl,
+                    void* workspace, uint64_t workspace_bytes, void* stream);
+uint64_t ipavsr_lstm_workspace_bytes(int N, int T, int H);
+
+/* ---- a4/a5/a7: fusion, merge, slice, dropout ---------------------------------------------------------- */
+/* out[M,F] = sum_s coeff_s * in_s[M,F]   (ElemwiseSumLayer; AdaptiveElemwiseSumLayer custom/layers.py:178-228).
+ * `ins` is a HOST array of S device pointers; coeffs is a DEVICE array of S floats or NULL (all ones). */
+int ipavsr_fuse_sum(const float* const* ins, const int* lds, int S, const float* coeffs, float* out, int ldo,
+                    int M, int F, void* stream);
+/* adasum backward: dcoeff[s] (+)= sum(dout * in_s) for every s (device array of S floats) */
+int ipavsr_adasum_bwd_coeff(const float* dout, int lddo, const float* const* ins, const int* lds, int S,
+                            float* dcoeff, int M, int F, int accumulate, void* stream);
+/* dst[:, col0:col0+F] (=|+=) alpha * src[:, :F]  — concat forward/backward and generic strided copy/axpy.
+ * alpha_dev (device scalar) may be NULL (alpha = 1). */
+int ipavsr_copy2d(const float* src, int lds, float* dst, int ldd, int M, int F, const float* alpha_dev,
+                  int accumulate, void* stream);
+/* SliceLayer(-1, axis=1): dst[n,:] = src[n*T + T-1, :] (fwd) ; scatter (bwd): dst[n*T+T-1,:] (+)= src[n,:] */
+int ipavsr_slice_last(const float* src, int lds, float* dst, int ldd, int N, int T, int F, int backward,
+                      int accumulate, void* stream);
+/* y = x * keep * scale (DropoutLayer with an explicit uint8 keep mask; same call is its backward) */
+int ipavsr_dropout(const float* x, int ldx, const uint8_t* keep, float* y, int ldy, int M, int F, float scale,
+                   void* stream);
+/* fills keep[M*F] with Bernoulli(1-p) from a counter-based generator (seed, offset) */
+int ipavsr_dropout_mask(uint8_t* keep, uint64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- a6: BatchNormLayer on (M,F), axes=(0,) (modelzoo/adenet_v1.py:82) ---------------------- */
+/* stats[0:F]=sum, stats[F:2F]=sum of squares over the M rows (for sync-BN these are all-reduced by the host) */
+int ipavsr_bn_stats(const float* x, int ldx, double* stats, int M, int F, void* stream);
+/* train: from (all-reduced) stats over M_total rows compute batch mean/inv_std into save_mean/save_istd, update
+ * running mean/inv_std with alpha, and write y.  deterministic: uses running mean/inv_std. */
+int ipavsr_bn_fwd(const float* x, int ldx, float* y, int ldy, const float* beta, const float* gamma,
+                  float* run_mean, float* run_istd, const double* stats, float* save_mean, float* save_istd,
+                  int M, int F, int64_t M_total, float eps, float alpha, int deterministic, int update_running,
+                  void* stream);
+/* bstats[0:F] = sum dy, bstats[F:2F] = sum dy*xhat (to be all-reduced for sync-BN) */
+int ipavsr_bn_bwd_stats(const float* dy, int lddy, const float* x, int ldx, const float* save_mean,
+                        const float* save_istd, double* bstats, int M, int F, void* stream);
+int ipavsr_bn_bwd(const float* dy, int lddy, const float* x, int ldx, const float* gamma,
+                  const float* save_mean, const float* save_istd, const double* bstats, float* dx, int lddx,
+                  float* dbeta, float* dgamma, int M, int F, int64_t M_total, int accumulate_params, void* stream);
+
+/* ---- a5/a8: softmax head + losses (custom/objectives.py:4-39; avletters/trimodal.py:327) ---------------- */
+/* probs = softmax(logits) row-wise over C columns */
+int ipavsr_softmax(const float* logits, int ldl, float* probs, int ldp, int M, int C, void* stream);
+/* frame-level: loss_sum[0] += -sum_r mask_r log softmax(probs_r)[y_r]  (the reference's double softmax) and
+ * dlogits = gradient of (loss_sum * inv_norm) w.r.t. the *pre-softmax* logits, through both softmaxes.
+ * The normaliser is inv_norm (host float) or, when count_dev != NULL, inv_norm / *count_dev with count_dev a
+ * DEVICE float holding the (all-reduced) global mask sum — data-parallel shards normalise by the global count
+ * without a host round trip. */
+int ipavsr_temporal_softmax_loss(const float* probs, int ldp, const int32_t* y, const uint8_t* mask,
+                                 float* loss_sum, float* dlogits, int lddl, int M, int C, float inv_norm,
+                                 const float* count_dev, void* stream);
+/* sequence-level: loss_sum[0] += -sum_n log probs[n,y_n]; dlogits = (probs - onehot) * inv_norm */
+int ipavsr_categorical_crossentropy(const float* probs, int ldp, const int32_t* y, float* loss_sum,
+                                    float* dlogits, int lddl, int M, int C, float inv_norm,
+                                    const float* count_dev, void* stream);
+
+/* ---- a9: update rules over a flat parameter arena ----------------------------------------------------- */
+/* One fused multi-tensor step over n floats.  lr_scale (device, n/segment granularity) is NULL for a single
+ * learning rate, else `seg_lr` is a device array giving the per-parameter-tensor learning rate and `seg_id`
+ * maps 256-float blocks to tensors (adam_vlr, custom/updates.py:35-99).
+ *   adam:     s1=m, s2=v;  step_scalar = sqrt(1-beta2^t)/(1-beta1^t) computed by the host in float32
+ *   adadelta: s1=E[g^2], s2=E[dx^2];  momentum/nesterov: s1=velocity */
+int ipavsr_optim_step(int kind, float* p, const float* g, float* s1, float* s2, uint64_t n,
+                      float lr, const float* seg_lr, const int32_t* seg_id, float step_scalar,
+                      float hp1, float hp2, float eps, float grad_scale, void* stream);
+
+/* ---- a10–a14: utils/preprocessing.py on device --------------------------------------------------------- */
+/* normalize_input (:218-242): per-frame (x-mean)/std, population std, in place allowed */
+int ipavsr_norm_samplewise(const float* x, int ldx, float* y, int ldy, int64_t frames, int D, void* stream);
+/* featurewise_normalize_sequence (:245-257): stats pass (mean[F], std[F] of x-mean) then apply (x-mean)/std */
+int ipavsr_norm_featurewise_stats(const float* x, int ldx, float* mean, float* std, double* scratch,
+                                  int64_t frames, int F, void* stream);
+int ipavsr_norm_featurewise_apply(const float* x, int ldx, const float* mean, const float* std, float* y,
+                                  int ldy, int64_t frames, int F, void* stream);
+/* sequencewise_mean_image_subtraction (:260-277): offsets[U+1] = prefix sums of the utterance lengths */
+int ipavsr_seq_mean_sub(const float* x, int ldx, float* y, int ldy, const int64_t* offsets, int U, int D,
+                        void* stream);
+/* compute_diff_images (:506-517) */
+int ipavsr_diff_image(const float* x, int ldx, float* y, int ldy, const int64_t* offsets, int U, int D,
+                      void* stream);
+/* concat_first_second_deltas (:465-489) with deltas (:17-51): y (frames, 3F) float64 = [x, d1, d2];
+ * max_len = the longest utterance (sizes the shared-memory tile) */
+int ipavsr_deltas_fir(const float* x, int ldx, double* y, int ldy, const int64_t* offsets, int U, int F, int w,
+                      int max_len, void* stream);
+
+/* ---- helpers ------------------------------------------------------------------------------------------ */
+int ipavsr_fill(float* p, uint64_t n, float v, void* stream);
+/* lo = x - tf32_trunc(x) (and optionally hi = tf32_trunc(x)) for the 3xTF32 GEMM mode */
+int ipavsr_tf32_split(const float* x, float* hi, float* lo, uint64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPAVSR_B200_H */

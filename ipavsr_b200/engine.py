@@ -1,0 +1,740 @@
+"""Device engine: executes a layer graph (ipavsr_b200.layers) forward and backward with the sm_100a kernels of
+libipavsr_b200.so.  This is what `theano.function(...)` + `T.grad` are in the reference
+(`runners/2stream_dct.py:263-279`): one call = forward (+ loss + full backward + update).
+
+PyTorch is used for device memory (caching allocator), streams and torch.distributed only.  Every number is
+produced by a kernel of this repository, called through the C-ABI with raw pointers on torch's current stream.
+There is no CPU fallback: without a CUDA device or the shared library the engine raises.
+
+Memory layout in HBM
+  * activations: row-major float32 matrices of N*T rows (row = n*T + t) with the leading dimension padded to a
+    multiple of 4 floats (16-byte rows for vector loads / TMA); a concat is never materialised — it is a list of
+    column segments that the consuming GEMM walks as a K-split.
+  * parameters: ONE flat float32 arena; each device tensor starts on a 256-float boundary.  Gradients and optimiser
+    state are arenas of the same layout, so the update is one fused kernel over the arena and the data-parallel
+    gradient all-reduce is one NCCL call.  LSTM gate matrices are stored stacked and gate-interleaved
+    (column 4u+g), which makes the hoisted input projection a single GEMM and the recurrence loads float4.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import layers as L
+
+ACT = {'linear': 0, 'sigmoid': 1, 'rectify': 2, 'tanh': 3, 'leaky_rectify': 4, 'very_leaky_rectify': 5,
+       'softplus': 6, 'elu': 7}
+GEMM_MODES = {'fp32': 0, 'tf32x3': 1, 'tf32': 2}
+OPT = {'adam': 0, 'adadelta': 1, 'sgd': 2, 'momentum': 3, 'nesterov': 4}
+GATES = ('ingate', 'forgetgate', 'cell', 'outgate')
+SEG = 256    # arena alignment in floats
+
+
+def _ld4(c):
+    return (int(c) + 3) // 4 * 4
+
+
+class DevMat(object):
+    """A (rows x cols) float32 device matrix with leading dimension ld; `t` keeps the storage alive."""
+    __slots__ = ('t', 'ptr', 'rows', 'cols', 'ld')
+
+    def __init__(self, t, ptr, rows, cols, ld):
+        self.t, self.ptr, self.rows, self.cols, self.ld = t, ptr, rows, cols, ld
+
+    def row_slice(self, r0, n):
+        return DevMat(self.t, self.ptr + 4 * r0 * self.ld, n, self.cols, self.ld)
+
+    def torch_view(self):
+        off = (self.ptr - self.t.data_ptr()) // 4
+        return self.t.view(-1)[off: off + (self.rows - 1) * self.ld + self.cols].as_strided(
+            (self.rows, self.cols), (self.ld, 1)) if self.rows > 0 else self.t.new_zeros((0, self.cols))
+
+
+class ParamArena(object):
+    """Flat device arena for every parameter of a network + the mapping Lasagne Param <-> device view."""
+
+    def __init__(self, layer_list, device):
+        self.device = device
+        self.tensors = {}      # key -> (offset, rows, cols, ld, trainable)
+        self.bind = {}         # Param -> (key, index function)
+        self.order = []
+        off = 0
+        aux = 0
+        self.aux_tensors = {}
+
+        def add(key, rows, cols, pad_ld=True):
+            nonlocal off
+            ld = _ld4(cols) if (pad_ld and rows > 1) else cols
+            self.tensors[key] = (off, rows, cols, ld)
+            self.order.append(key)
+            off += (rows * ld + SEG - 1) // SEG * SEG
+
+        def add_aux(key, n):
+            nonlocal aux
+            self.aux_tensors[key] = (aux, n)
+            aux += (n + 3) // 4 * 4
+
+        for l in layer_list:
+            if isinstance(l, L.DenseLayer):
+                add((l, 'W'), l.W.shape[0], l.W.shape[1])
+                self.bind[l.W] = ((l, 'W'), None)
+                if l.b is not None:
+                    add((l, 'b'), 1, l.b.shape[0])
+                    self.bind[l.b] = ((l, 'b'), None)
+            elif isinstance(l, L.LSTMLayer):
+                H, I = l.num_units, l.num_inputs
+                add((l, 'W_in'), I, 4 * H)
+                add((l, 'W_hid'), H, 4 * H)
+                add((l, 'b'), 1, 4 * H)
+                for g, name in enumerate(GATES):
+                    self.bind[getattr(l, 'W_in_to_' + name)] = ((l, 'W_in'), ('gate', g))
+                    self.bind[getattr(l, 'W_hid_to_' + name)] = ((l, 'W_hid'), ('gate', g))
+                    self.bind[getattr(l, 'b_' + name)] = ((l, 'b'), ('gate', g))
+                if l.peepholes:
+                    add((l, 'peep'), 3, H, pad_ld=False)
+                    self.bind[l.W_cell_to_ingate] = ((l, 'peep'), ('row', 0))
+                    self.bind[l.W_cell_to_forgetgate] = ((l, 'peep'), ('row', 1))
+                    self.bind[l.W_cell_to_outgate] = ((l, 'peep'), ('row', 2))
+                add((l, 'cell_init'), 1, H)
+                add((l, 'hid_init'), 1, H)
+                self.bind[l.cell_init] = ((l, 'cell_init'), None)
+                self.bind[l.hid_init] = ((l, 'hid_init'), None)
+            elif isinstance(l, L.BatchNormLayer):
+                F = l.beta.shape[0]
+                add((l, 'beta'), 1, F)
+                add((l, 'gamma'), 1, F)
+                self.bind[l.beta] = ((l, 'beta'), None)
+                self.bind[l.gamma] = ((l, 'gamma'), None)
+                add_aux((l, 'mean'), F)
+                add_aux((l, 'inv_std'), F)
+                self.bind[l.mean] = ((l, 'mean'), 'aux')
+                self.bind[l.inv_std] = ((l, 'inv_std'), 'aux')
+            elif isinstance(l, L.AdaptiveElemwiseSumLayer):
+                add((l, 'coeffs'), 1, len(l.coeffs))
+                for i, c in enumerate(l.coeffs):
+                    self.bind[c] = ((l, 'coeffs'), ('elem', i))
+        self.n = off
+        self.tail = off                 # [tail+0] = loss sum, [tail+1] = normaliser count
+        total = off + SEG
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=device)
+        self.aux = torch.zeros(max(aux, 4), dtype=torch.float32, device=device)
+        self.state = {}
+        # upload host masters, then bind
+        params = list(self.bind.keys())
+        for p in params:
+            self._view(self.flat, p).copy_(torch.from_numpy(np.ascontiguousarray(p._host)).reshape(
+                self._view(self.flat, p).shape))
+        for p in params:
+            p._binding = (self, p)
+
+    # -- views ------------------------------------------------------------------------------------------
+    def mat(self, key, which='flat'):
+        off, rows, cols, ld = self.tensors[key]
+        buf = getattr(self, which) if isinstance(which, str) else which
+        return DevMat(buf, buf.data_ptr() + 4 * off, rows, cols, ld)
+
+    def aux_ptr(self, key):
+        off, n = self.aux_tensors[key]
+        return self.aux.data_ptr() + 4 * off
+
+    def _view(self, buf, p):
+        key, idx = self.bind[p]
+        if idx == 'aux':
+            off, n = self.aux_tensors[key]
+            return self.aux[off: off + n]
+        off, rows, cols, ld = self.tensors[key]
+        m = buf[off: off + rows * ld].view(rows, ld)[:, :cols]
+        if idx is None:
+            if rows == 1:
+                return m[0, 0] if p.shape == () else m[0].view(p.shape)
+            return m
+        kind, k = idx
+        if kind == 'gate':
+            return m[:, k::4] if rows > 1 or len(p.shape) == 2 else m[0, k::4]
+        if kind == 'row':
+            return m[k]
+        if kind == 'elem':
+            return m[0, k]
+        raise KeyError(idx)
+
+    def read(self, p, which='flat'):
+        buf = getattr(self, which)
+        return self._view(buf, p).detach().cpu().numpy().astype(np.float32).reshape(p.shape).copy()
+
+    def write(self, p, value):
+        v = self._view(self.flat, p)
+        v.copy_(torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32)).reshape(v.shape))
+
+    def opt_state(self, name):
+        if name not in self.state:
+            self.state[name] = torch.zeros_like(self.flat)
+        return self.state[name]
+
+    def tensor_of(self, p):
+        return self.bind[p][0]
+
+
+class _Run(object):
+    """Per-call state: values, saved tensors for backward, gradients."""
+
+    def __init__(self, N, T):
+        self.N, self.T = N, T
+        self.vals = {}
+        self.saved = {}
+        self.grads = {}
+
+
+class Engine(object):
+    def __init__(self, output_layer, device=None, gemm_mode=None, lstm_impl=None, delta_exact=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('ipavsr_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self.out = output_layer
+        self.layers = L.get_all_layers(output_layer)
+        self.gemm_mode = GEMM_MODES[gemm_mode or os.environ.get('IPAVSR_GEMM_MODE', 'fp32')]
+        self.lstm_impl = int(os.environ.get('IPAVSR_LSTM_IMPL', '0')) if lstm_impl is None else int(lstm_impl)
+        self.delta_exact = int(os.environ.get('IPAVSR_DELTA_EXACT', '1')) if delta_exact is None else int(delta_exact)
+        with torch.cuda.device(self.device):
+            self.arena = ParamArena(self.layers, self.device)
+        self.requires_grad = {}
+        for l in self.layers:
+            ins = getattr(l, 'input_layers', None) or ([l.input_layer] if getattr(l, 'input_layer', None) else [])
+            self.requires_grad[l] = bool(l.params) or any(self.requires_grad.get(i, False) for i in ins if i is not None)
+        self.input_layers = [l for l in self.layers if isinstance(l, L.InputLayer)]
+        self.mask_layers = set()
+        for l in self.layers:
+            if isinstance(l, L.LSTMLayer) and l.mask_incoming_index > 0:
+                self.mask_layers.add(l.input_layers[1])
+        self.dropout_seed = 1234
+        self.dropout_calls = 0
+        self.world = None            # (rank, world_size, group) when data-parallel
+        self.step_t = np.float32(0)  # Adam's shared step counter (custom/updates.py:74)
+        self._ws = None
+        self._gemm_ws = None
+        self._lr_cache = None
+
+    # ------------------------------------------------------------------------------------------------
+    # small helpers
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def new(self, rows, cols, zero=False):
+        ld = _ld4(cols)
+        n = max(rows * ld, 4)
+        t = (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=self.device)
+        return DevMat(t, t.data_ptr(), rows, cols, ld)
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() * 4 < nbytes:
+            self._ws = torch.empty((int(nbytes) + 3) // 4, dtype=torch.float32, device=self.device)
+        return self._ws
+
+    def gemm(self, A, B, Cm, M, N, K, transA=0, transB=0, bias=None, act=0, accumulate=0):
+        ws_ptr, ws_bytes = None, 0
+        if self.gemm_mode != 0:
+            need = self.lib.ipavsr_gemm_workspace_bytes(self.gemm_mode, transA, transB, M, N, K)
+            if need:
+                if self._gemm_ws is None or self._gemm_ws.numel() * 4 < need:
+                    self._gemm_ws = torch.empty((int(need) + 3) // 4, dtype=torch.float32, device=self.device)
+                ws_ptr, ws_bytes = self._gemm_ws.data_ptr(), int(need)
+        _lib.call('ipavsr_gemm', self.gemm_mode, transA, transB, M, N, K, A.ptr, A.ld, B.ptr, B.ld, Cm.ptr, Cm.ld,
+                  bias, act, accumulate, ws_ptr, ws_bytes, self.stream)
+
+    def _proj(self, segs, W, out, bias, act):
+        """out = act( [segs...] @ W + bias ): the concat is walked as a K-split accumulate."""
+        k0 = 0
+        for i, a in enumerate(segs):
+            last = i == len(segs) - 1
+            self.gemm(a, W.row_slice(k0, a.cols), out, a.rows, out.cols, a.cols, 0, 0,
+                      bias if last else None, act if last else 0, 1 if i > 0 else 0)
+            k0 += a.cols
+
+    # ------------------------------------------------------------------------------------------------
+    # input staging
+    # ------------------------------------------------------------------------------------------------
+    def _upload(self, arr, kind):
+        if isinstance(arr, torch.Tensor):
+            t = arr
+        else:
+            a = np.asarray(arr)
+            if kind == 'mask':
+                a = np.ascontiguousarray(a.astype(np.uint8, copy=False))
+            elif kind == 'int':
+                a = np.ascontiguousarray(a.astype(np.int32, copy=False))
+            else:
+                a = np.ascontiguousarray(a.astype(np.float32, copy=False))       # allow_input_downcast
+            t = torch.from_numpy(a)
+        if kind == 'mask':
+            return t.to(torch.uint8).to(self.device, non_blocking=True).contiguous()
+        if kind == 'int':
+            return t.to(torch.int32).to(self.device, non_blocking=True).contiguous()
+        t = t.to(torch.float32)
+        N, T, F = t.shape
+        ld = _ld4(F)
+        if ld == F:
+            d = t.to(self.device, non_blocking=True).contiguous()
+            return DevMat(d, d.data_ptr(), N * T, F, F)
+        d = torch.zeros(N * T, ld, dtype=torch.float32, device=self.device)
+        d[:, :F].copy_(t.reshape(N * T, F), non_blocking=True)
+        return DevMat(d, d.data_ptr(), N * T, F, ld)
+
+    # ------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, inputs, window, deterministic=True, train=False, dropout_masks=None, update_bn=True):
+        """inputs: {InputLayer: array}.  Returns (_Run, output Val).  `train` keeps what backward needs."""
+        lib, st = self.lib, self.stream
+        first = None
+        for l in self.input_layers:
+            if l not in self.mask_layers:
+                first = inputs[l]
+                break
+        N, T = int(first.shape[0]), int(first.shape[1])
+        run = _Run(N, T)
+        run.window = int(window) if window is not None else 0
+        run.deterministic = deterministic
+        ar = self.arena
+        for l in self.layers:
+            if isinstance(l, L.InputLayer):
+                if l in self.mask_layers:
+                    run.vals[l] = self._upload(inputs[l], 'mask')
+                else:
+                    run.vals[l] = [self._upload(inputs[l], 'float')]
+            elif isinstance(l, L.ReshapeLayer):
+                run.vals[l] = run.vals[l.input_layer]
+            elif isinstance(l, L.DenseLayer):
+                segs = run.vals[l.input_layer]
+                rows = segs[0].rows
+                W = ar.mat((l, 'W'))
+                b = ar.mat((l, 'b')).ptr if l.b is not None else None
+                out = self.new(rows, l.num_units)
+                if l.nonlinearity.name == 'softmax':
+                    logits = self.new(rows, l.num_units)
+                    self._proj(segs, W, logits, b, 0)
+                    _lib.call('ipavsr_softmax', logits.ptr, logits.ld, out.ptr, out.ld, rows, l.num_units, st)
+                else:
+                    self._proj(segs, W, out, b, ACT[l.nonlinearity.name])
+                run.vals[l] = [out]
+            elif isinstance(l, L.BatchNormLayer):
+                x = run.vals[l.input_layer][0]
+                F = x.cols
+                y = self.new(x.rows, F)
+                beta, gamma = ar.mat((l, 'beta')).ptr, ar.mat((l, 'gamma')).ptr
+                rm, ri = ar.aux_ptr((l, 'mean')), ar.aux_ptr((l, 'inv_std'))
+                if deterministic:
+                    _lib.call('ipavsr_bn_fwd', x.ptr, x.ld, y.ptr, y.ld, beta, gamma, rm, ri, None, None, None,
+                              x.rows, F, 0, l.epsilon, l.alpha, 1, 0, st)
+                else:
+                    stats = torch.empty(2 * F, dtype=torch.float64, device=self.device)
+                    save = torch.empty(2 * F, dtype=torch.float32, device=self.device)
+                    _lib.call('ipavsr_bn_stats', x.ptr, x.ld, stats.data_ptr(), x.rows, F, st)
+                    m_total = x.rows
+                    if self.world is not None:
+                        torch.distributed.all_reduce(stats, group=self.world[2])
+                        m_total = x.rows * self.world[1]
+                    _lib.call('ipavsr_bn_fwd', x.ptr, x.ld, y.ptr, y.ld, beta, gamma, rm, ri, stats.data_ptr(),
+                              save.data_ptr(), save.data_ptr() + 4 * F, x.rows, F, m_total, l.epsilon, l.alpha, 0,
+                              1 if update_bn else 0, st)
+                    run.saved[l] = (save, m_total)
+                run.vals[l] = [y]
+            elif isinstance(l, L.DropoutLayer):
+                segs = run.vals[l.input_layer]
+                if deterministic:
+                    run.vals[l] = segs
+                else:
+                    rows = segs[0].rows
+                    tot = sum(s.cols for s in segs)
+                    if dropout_masks is not None and l.name in dropout_masks:
+                        keep_full = torch.from_numpy(np.ascontiguousarray(
+                            np.asarray(dropout_masks[l.name]).reshape(rows, tot).astype(np.uint8))).to(self.device)
+                    else:
+                        keep_full = torch.empty(rows, tot, dtype=torch.uint8, device=self.device)
+                        _lib.call('ipavsr_dropout_mask', keep_full.data_ptr(), rows * tot, float(l.p),
+                                  self.dropout_seed, self.dropout_calls << 32, st)
+                        self.dropout_calls += 1
+                    scale = 1.0 / (1.0 - l.p) if l.rescale else 1.0
+                    outs, keeps, c0 = [], [], 0
+                    for s in segs:
+                        k = keep_full[:, c0:c0 + s.cols].contiguous()
+                        o = self.new(rows, s.cols)
+                        _lib.call('ipavsr_dropout', s.ptr, s.ld, k.data_ptr(), o.ptr, o.ld, rows, s.cols, scale, st)
+                        outs.append(o)
+                        keeps.append(k)
+                        c0 += s.cols
+                    run.saved[l] = (keeps, scale)
+                    run.vals[l] = outs
+            elif isinstance(l, L.DeltaLayer):
+                x = self._single(run.vals[l.input_layer])
+                y = self.new(x.rows, 3 * x.cols)
+                _lib.call('ipavsr_delta_fwd', x.ptr, x.ld, y.ptr, y.ld, N, T, x.cols, run.window, self.delta_exact, st)
+                run.vals[l] = [y]
+            elif isinstance(l, L.LSTMLayer):
+                segs = run.vals[l.input_layers[0]]
+                H = l.num_units
+                if l.mask_incoming_index > 0:
+                    mask = run.vals[l.input_layers[1]]
+                else:
+                    mask = torch.ones(N, T, dtype=torch.uint8, device=self.device)
+                xw = self.new(N * T, 4 * H)
+                self._proj(segs, ar.mat((l, 'W_in')), xw, ar.mat((l, 'b')).ptr, 0)
+                out = self.new(N * T, H, zero=(_ld4(H) != H))
+                gates = cell = hprev = None
+                if train:
+                    gates = self.new(N * T, 4 * H)
+                    cell = self.new(N * T, H)
+                    hprev = self.new(N * T, H, zero=(_ld4(H) != H))
+                    if cell.ld != H:       # cell is dense (ld = H) inside the kernels
+                        cell = DevMat(cell.t, cell.ptr, N * T, H, H)
+                peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
+                nbytes = lib.ipavsr_lstm_workspace_bytes(N, T, H)
+                ws = self._workspace(nbytes)
+                _lib.call('ipavsr_lstm_fwd', xw.ptr, ar.mat((l, 'W_hid')).ptr, peep, ar.mat((l, 'cell_init')).ptr,
+                          ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
+                          gates.ptr if gates else None, cell.ptr if cell else None, hprev.ptr if hprev else None,
+                          N, T, H, out.ld, 1 if l.backwards else 0, self.lstm_impl, ws.data_ptr(), int(nbytes), st)
+                run.saved[l] = (mask, gates, cell, hprev)
+                run.vals[l] = [out]
+            elif isinstance(l, (L.ElemwiseSumLayer, L.AdaptiveElemwiseSumLayer)):
+                ins = [self._single(run.vals[i]) for i in l.input_layers]
+                rows, F = ins[0].rows, ins[0].cols
+                out = self.new(rows, F, zero=(_ld4(F) != F))
+                ptrs = (C.c_void_p * len(ins))(*[i.ptr for i in ins])
+                lds = (C.c_int * len(ins))(*[i.ld for i in ins])
+                coeffs = ar.mat((l, 'coeffs')).ptr if isinstance(l, L.AdaptiveElemwiseSumLayer) else None
+                _lib.call('ipavsr_fuse_sum', ptrs, lds, len(ins), coeffs, out.ptr, out.ld, rows, F, st)
+                run.vals[l] = [out]
+            elif isinstance(l, L.ConcatLayer):
+                segs = []
+                for i in l.input_layers:
+                    segs.extend(run.vals[i])
+                run.vals[l] = segs
+            elif isinstance(l, L.SliceLayer):
+                x = self._single(run.vals[l.input_layer])
+                out = self.new(N, x.cols, zero=(_ld4(x.cols) != x.cols))
+                _lib.call('ipavsr_slice_last', x.ptr, x.ld, out.ptr, out.ld, N, T, x.cols, 0, 0, st)
+                run.vals[l] = [out]
+            else:
+                raise TypeError('unsupported layer type %s' % type(l).__name__)
+        return run, run.vals[self.out]
+
+    def _single(self, segs):
+        if len(segs) == 1:
+            return segs[0]
+        rows = segs[0].rows
+        tot = sum(s.cols for s in segs)
+        out = self.new(rows, tot, zero=True)
+        c0 = 0
+        for s in segs:
+            _lib.call('ipavsr_copy2d', s.ptr, s.ld, out.ptr + 4 * c0, out.ld, rows, s.cols, None, 0, self.stream)
+            c0 += s.cols
+        return out
+
+    def read(self, segs):
+        """Val -> host ndarray (rows, cols)."""
+        return np.concatenate([s.torch_view().detach().cpu().numpy() for s in segs], axis=1)
+
+    # ------------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------------
+    def _grad_target(self, run, layer, like):
+        """Buffers to write d(layer output) into: (segs, accumulate flag)."""
+        if layer in run.grads:
+            segs, owned = run.grads[layer]
+            if not owned:
+                new = [self.new(s.rows, s.cols, zero=(_ld4(s.cols) != s.cols)) for s in segs]
+                for a, b in zip(segs, new):
+                    _lib.call('ipavsr_copy2d', a.ptr, a.ld, b.ptr, b.ld, a.rows, a.cols, None, 0, self.stream)
+                run.grads[layer] = (new, True)
+                segs = new
+            return segs, 1
+        segs = [self.new(s.rows, s.cols, zero=(_ld4(s.cols) != s.cols)) for s in like]
+        run.grads[layer] = (segs, True)
+        return segs, 0
+
+    def _pass_grad(self, run, layer, segs):
+        if layer is None or not self.requires_grad.get(layer, False):
+            return
+        if layer not in run.grads:
+            run.grads[layer] = (segs, False)
+            return
+        dst, _ = self._grad_target(run, layer, segs)
+        for a, b in zip(segs, dst):
+            _lib.call('ipavsr_copy2d', a.ptr, a.ld, b.ptr, b.ld, a.rows, a.cols, None, 1, self.stream)
+
+    def backward(self, run, dlogits):
+        """dlogits: DevMat gradient w.r.t. the pre-softmax logits of the output Dense.  Writes the gradient arena."""
+        lib, st, ar = self.lib, self.stream, self.arena
+        N, T = run.N, run.T
+        G = lambda key: ar.mat(key, 'grad')
+        head = self.out
+        while isinstance(head, L.ReshapeLayer):
+            head = head.input_layer
+        if not (isinstance(head, L.DenseLayer) and head.nonlinearity.name == 'softmax'):
+            raise ValueError('the network output must be a softmax DenseLayer to train')
+        run.grads[head] = ([dlogits], True)
+        for l in reversed(self.layers):
+            if l not in run.grads or isinstance(l, L.InputLayer):
+                continue
+            gsegs, _ = run.grads[l]
+            if isinstance(l, L.ReshapeLayer):
+                self._pass_grad(run, l.input_layer, gsegs)
+            elif isinstance(l, L.DenseLayer):
+                dY = gsegs[0]
+                xin = run.vals[l.input_layer]
+                rows, Nout = dY.rows, l.num_units
+                if l.nonlinearity.name == 'softmax':
+                    dZ = dY          # the loss kernel already went through the softmax
+                    if l.b is not None:
+                        _lib.call('ipavsr_colsum', dZ.ptr, dZ.ld, G((l, 'b')).ptr, rows, Nout, 0, st)
+                else:
+                    dZ = dY if run.grads[l][1] else self.new(rows, Nout)
+                    y = run.vals[l][0]
+                    _lib.call('ipavsr_dense_bwd_prep', dY.ptr, dY.ld, y.ptr, y.ld, dZ.ptr, dZ.ld,
+                              G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0, st)
+                self._proj_bwd(run, l.input_layer, xin, dZ, ar.mat((l, 'W')), G((l, 'W')))
+            elif isinstance(l, L.BatchNormLayer):
+                dy = gsegs[0]
+                x = run.vals[l.input_layer][0]
+                F = x.cols
+                save, m_total = run.saved[l]
+                bst = torch.empty(2 * F, dtype=torch.float64, device=self.device)
+                _lib.call('ipavsr_bn_bwd_stats', dy.ptr, dy.ld, x.ptr, x.ld, save.data_ptr(), save.data_ptr() + 4 * F,
+                          bst.data_ptr(), x.rows, F, st)
+                if self.world is not None:
+                    torch.distributed.all_reduce(bst, group=self.world[2])
+                dx = self.new(x.rows, F)
+                _lib.call('ipavsr_bn_bwd', dy.ptr, dy.ld, x.ptr, x.ld, ar.mat((l, 'gamma')).ptr, save.data_ptr(),
+                          save.data_ptr() + 4 * F, bst.data_ptr(), dx.ptr, dx.ld, G((l, 'beta')).ptr,
+                          G((l, 'gamma')).ptr, x.rows, F, m_total, 0, st)
+                if self.world is not None:      # beta/gamma grads are already global sums: undo the later all-reduce
+                    for key in ((l, 'beta'), (l, 'gamma')):
+                        G(key).torch_view().mul_(1.0 / self.world[1])
+                self._pass_grad(run, l.input_layer, [dx])
+            elif isinstance(l, L.DropoutLayer):
+                if l in run.saved:
+                    keeps, scale = run.saved[l]
+                    outs = []
+                    for g, k in zip(gsegs, keeps):
+                        o = self.new(g.rows, g.cols)
+                        _lib.call('ipavsr_dropout', g.ptr, g.ld, k.data_ptr(), o.ptr, o.ld, g.rows, g.cols, scale, st)
+                        outs.append(o)
+                    gsegs = outs
+                self._pass_grad(run, l.input_layer, gsegs)
+            elif isinstance(l, L.DeltaLayer):
+                if self.requires_grad.get(l.input_layer, False):
+                    g = gsegs[0]
+                    F = g.cols // 3
+                    tgt, acc = self._grad_target(run, l.input_layer, [DevMat(None, 0, g.rows, F, _ld4(F))])
+                    _lib.call('ipavsr_delta_bwd', g.ptr, g.ld, tgt[0].ptr, tgt[0].ld, N, T, F, run.window, acc, st)
+            elif isinstance(l, L.LSTMLayer):
+                dout = gsegs[0]
+                H = l.num_units
+                mask, gates, cell, hprev = run.saved[l]
+                dG = self.new(N * T, 4 * H)
+                peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
+                dpeep = G((l, 'peep')).ptr if l.peepholes else None
+                nbytes = lib.ipavsr_lstm_workspace_bytes(N, T, H)
+                ws = self._workspace(nbytes)
+                clip = l.grad_clipping if l.grad_clipping else 0.0
+                _lib.call('ipavsr_lstm_bwd', dout.ptr, ar.mat((l, 'W_hid')).ptr, peep, ar.mat((l, 'cell_init')).ptr,
+                          mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,
+                          G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
+                          self.lstm_impl, ws.data_ptr(), int(nbytes), st)
+                if not l.learn_init:
+                    G((l, 'cell_init')).torch_view().zero_()
+                    G((l, 'hid_init')).torch_view().zero_()
+                _lib.call('ipavsr_colsum', dG.ptr, dG.ld, G((l, 'b')).ptr, N * T, 4 * H, 0, st)
+                # dW_hid = hprev^T dG
+                self.gemm(hprev, dG, G((l, 'W_hid')), H, 4 * H, N * T, transA=1)
+                self._proj_bwd(run, l.input_layers[0], run.vals[l.input_layers[0]], dG, ar.mat((l, 'W_in')),
+                               G((l, 'W_in')))
+            elif isinstance(l, L.AdaptiveElemwiseSumLayer):
+                g = gsegs[0]
+                ins = [self._single(run.vals[i]) for i in l.input_layers]
+                ptrs = (C.c_void_p * len(ins))(*[i.ptr for i in ins])
+                lds = (C.c_int * len(ins))(*[i.ld for i in ins])
+                _lib.call('ipavsr_adasum_bwd_coeff', g.ptr, g.ld, ptrs, lds, len(ins), G((l, 'coeffs')).ptr, g.rows,
+                          g.cols, 0, st)
+                coeffs = ar.mat((l, 'coeffs'))
+                for k, i in enumerate(l.input_layers):
+                    if not self.requires_grad.get(i, False):
+                        continue
+                    tgt, acc = self._grad_target(run, i, [g])
+                    _lib.call('ipavsr_copy2d', g.ptr, g.ld, tgt[0].ptr, tgt[0].ld, g.rows, g.cols,
+                              coeffs.ptr + 4 * k, acc, st)
+            elif isinstance(l, L.ElemwiseSumLayer):
+                for i in l.input_layers:
+                    self._pass_grad(run, i, gsegs)
+            elif isinstance(l, L.ConcatLayer):
+                k = 0
+                for i in l.input_layers:
+                    n = len(run.vals[i])
+                    self._pass_grad(run, i, gsegs[k:k + n])
+                    k += n
+            elif isinstance(l, L.SliceLayer):
+                g = gsegs[0]
+                x = run.vals[l.input_layer][0]
+                if l.input_layer in run.grads:
+                    tgt, acc = self._grad_target(run, l.input_layer, [x])
+                else:
+                    full = self.new(x.rows, x.cols, zero=True)
+                    run.grads[l.input_layer] = ([full], True)
+                    tgt, acc = [full], 1
+                _lib.call('ipavsr_slice_last', g.ptr, g.ld, tgt[0].ptr, tgt[0].ld, N, T, x.cols, 1, acc, st)
+            else:
+                raise TypeError('unsupported layer type %s' % type(l).__name__)
+            del run.grads[l]
+
+    def _proj_bwd(self, run, in_layer, xsegs, dZ, W, dW):
+        """dW[rows of seg] = seg^T dZ ;  d(seg) (+)= dZ W[rows of seg]^T."""
+        need_dx = self.requires_grad.get(in_layer, False)
+        tgt = acc = None
+        if need_dx:
+            tgt, acc = self._grad_target(run, in_layer, xsegs)
+        k0 = 0
+        for i, a in enumerate(xsegs):
+            self.gemm(a, dZ, dW.row_slice(k0, a.cols), a.cols, dZ.cols, a.rows, transA=1)
+            if need_dx:
+                self.gemm(dZ, W.row_slice(k0, a.cols), tgt[i], a.rows, a.cols, dZ.cols, transB=1, accumulate=acc)
+            k0 += a.cols
+
+    # ------------------------------------------------------------------------------------------------
+    # loss + step
+    # ------------------------------------------------------------------------------------------------
+    def loss_and_backward(self, run, probs, loss, y, mask, count=None):
+        """Runs the loss kernel (writes loss sum into the gradient arena tail) and the full backward."""
+        st, ar = self.stream, self.arena
+        p = probs[0]
+        tail = ar.grad.data_ptr() + 4 * ar.tail
+        ar.grad[ar.tail: ar.tail + 4].zero_()
+        if self.world is not None:
+            ar.grad[ar.tail + 2: ar.tail + 3].fill_(1.0)     # sums to world_size in the gradient all-reduce
+        dlogits = self.new(p.rows, p.cols)
+        yd = self._upload(y, 'int')
+        count_dev = None
+        if loss == 'temporal_softmax':
+            md = mask if isinstance(mask, torch.Tensor) and mask.is_cuda else self._upload(mask, 'mask')
+            if count is None:
+                count = float(np.asarray(mask).sum()) if not isinstance(mask, torch.Tensor) else None
+            if count is None or self.world is not None:
+                cnt = md.sum(dtype=torch.float32).reshape(1)
+                if self.world is not None:
+                    torch.distributed.all_reduce(cnt, group=self.world[2])
+                ar.grad[ar.tail + 1: ar.tail + 2].copy_(cnt)
+                count_dev, inv = tail + 4, 1.0
+            else:
+                ar.grad[ar.tail + 1: ar.tail + 2].fill_(count)
+                inv = 1.0 / count
+            _lib.call('ipavsr_temporal_softmax_loss', p.ptr, p.ld, yd.data_ptr(), md.data_ptr(), tail, dlogits.ptr,
+                      dlogits.ld, p.rows, p.cols, inv, count_dev, st)
+        elif loss == 'categorical_crossentropy':
+            n_glob = p.rows * (self.world[1] if self.world is not None else 1)
+            ar.grad[ar.tail + 1: ar.tail + 2].fill_(float(n_glob))
+            _lib.call('ipavsr_categorical_crossentropy', p.ptr, p.ld, yd.data_ptr(), tail, dlogits.ptr, dlogits.ld,
+                      p.rows, p.cols, 1.0 / n_glob, None, st)
+        else:
+            raise ValueError('unknown loss %r' % (loss,))
+        self.backward(run, dlogits)
+
+    def loss_only(self, probs, loss, y, mask):
+        st = self.stream
+        p = probs[0]
+        buf = torch.zeros(4, dtype=torch.float32, device=self.device)
+        yd = self._upload(y, 'int')
+        if loss == 'temporal_softmax':
+            md = self._upload(mask, 'mask')
+            cnt = md.sum(dtype=torch.float32).reshape(1)
+            _lib.call('ipavsr_temporal_softmax_loss', p.ptr, p.ld, yd.data_ptr(), md.data_ptr(), buf.data_ptr(), None,
+                      0, p.rows, p.cols, 1.0, None, st)
+            both = torch.stack([buf[0], cnt[0]])
+        else:
+            _lib.call('ipavsr_categorical_crossentropy', p.ptr, p.ld, yd.data_ptr(), buf.data_ptr(), None, 0, p.rows,
+                      p.cols, 1.0, None, st)
+            both = torch.stack([buf[0], torch.tensor(float(p.rows), device=self.device)])
+        if self.world is not None:
+            torch.distributed.all_reduce(both, group=self.world[2])
+        h = both.cpu().numpy()
+        return np.float32(h[0] / h[1])
+
+    def allreduce_grads(self):
+        if self.world is not None:
+            torch.distributed.all_reduce(self.arena.grad, group=self.world[2])
+
+    def read_loss(self):
+        ar = self.arena
+        h = ar.grad[ar.tail: ar.tail + 3].cpu().numpy()
+        w = h[2] if h[2] > 0 else 1.0      # the (already global) count was summed world_size times
+        return np.float32(h[0] / (h[1] / w))
+
+    def optim_step(self, kind, lr, params=None, lr_map=None, **hp):
+        ar, st = self.arena, self.stream
+        n = ar.n
+        seg_lr = seg_id = None
+        if lr_map is not None:
+            seg_lr, seg_id = self._lr_tables(lr_map, params)
+        if kind == 'adam':
+            b1, b2, eps = np.float32(hp.get('beta1', 0.9)), np.float32(hp.get('beta2', 0.999)), hp.get('epsilon', 1e-8)
+            one = np.float32(1)
+            self.step_t = np.float32(self.step_t + one)
+            scalar = float(np.sqrt(one - b2 ** self.step_t) / (one - b1 ** self.step_t))
+            _lib.call('ipavsr_optim_step', OPT['adam'], ar.flat.data_ptr(), ar.grad.data_ptr(),
+                      ar.opt_state('m').data_ptr(), ar.opt_state('v').data_ptr(), n, float(lr),
+                      seg_lr, seg_id, scalar, float(b1), float(b2), float(eps), 1.0, st)
+        elif kind == 'adadelta':
+            _lib.call('ipavsr_optim_step', OPT['adadelta'], ar.flat.data_ptr(), ar.grad.data_ptr(),
+                      ar.opt_state('acc').data_ptr(), ar.opt_state('dacc').data_ptr(), n, float(lr), seg_lr, seg_id,
+                      1.0, float(hp.get('rho', 0.95)), 0.0, float(hp.get('epsilon', 1e-6)), 1.0, st)
+        elif kind == 'sgd':
+            _lib.call('ipavsr_optim_step', OPT['sgd'], ar.flat.data_ptr(), ar.grad.data_ptr(), None, None, n,
+                      float(lr), seg_lr, seg_id, 1.0, 0.0, 0.0, 0.0, 1.0, st)
+        elif kind in ('momentum', 'nesterov'):
+            _lib.call('ipavsr_optim_step', OPT[kind], ar.flat.data_ptr(), ar.grad.data_ptr(),
+                      ar.opt_state('vel').data_ptr(), None, n, float(lr), seg_lr, seg_id, 1.0,
+                      float(hp.get('momentum', 0.9)), 0.0, 0.0, 1.0, st)
+        else:
+            raise ValueError('unknown update rule %r' % (kind,))
+
+    def _lr_tables(self, lr_map, params):
+        """Per-tensor learning rates (adam_vlr, custom/updates.py:83): a device table indexed by 256-float block."""
+        ar = self.arena
+        key = tuple(sorted((p.name, float(v.get_value() if hasattr(v, 'get_value') else v)) for p, v in lr_map.items()))
+        if self._lr_cache is not None and self._lr_cache[0] == key:
+            return self._lr_cache[1], self._lr_cache[2]
+        per_tensor = {}
+        for p, v in lr_map.items():
+            v = v.get_value() if hasattr(v, 'get_value') else v
+            k = ar.tensor_of(p)
+            if k in per_tensor and per_tensor[k] != float(v):
+                raise ValueError('parameters sharing the device tensor %r need one learning rate' % (k,))
+            per_tensor[k] = float(v)
+        ids = np.zeros(ar.n // SEG + 1, dtype=np.int32)
+        lrs = np.zeros(len(ar.order) + 1, dtype=np.float32)
+        for i, k in enumerate(ar.order):
+            off, rows, cols, ld = ar.tensors[k]
+            nblk = (rows * ld + SEG - 1) // SEG
+            ids[off // SEG: off // SEG + nblk] = i
+            lrs[i] = per_tensor.get(k, 0.0)
+        seg_id = torch.from_numpy(ids).to(self.device)
+        seg_lr = torch.from_numpy(lrs).to(self.device)
+        self._lr_cache = (key, seg_lr.data_ptr(), seg_id.data_ptr(), seg_lr, seg_id)
+        return seg_lr.data_ptr(), seg_id.data_ptr()
+
+    def param_grads(self, params=None):
+        """Host copies of the gradients in Lasagne parameter order (tests)."""
+        params = params if params is not None else L.get_all_params(self.out, trainable=True)
+        return [self.arena.read(p, 'grad') for p in params]
+
+
+def get_engine(output_layer, **kw):
+    """One engine (one parameter arena) per output layer, shared by every compiled function."""
+    eng = getattr(output_layer, '_ipavsr_engine', None)
+    if eng is None:
+        eng = Engine(output_layer, **kw)
+        output_layer._ipavsr_engine = eng
+    return eng

@@ -1,0 +1,154 @@
+"""The compile step of the reference runners, mirrored: `theano.function(inputs, outputs, updates=...)`
+(`runners/2stream_dct.py:268-279`) becomes `ipavsr_b200.function(inputs, outputs, updates=...)`, returning a
+callable with the same positional arguments that runs the B200 engine.
+
+    predictions = layers.get_output(network, deterministic=False)
+    cost = temporal_softmax_loss(predictions, targets, mask)
+    updates = adam(cost, all_params, learning_rate=lr)
+    train = function([inputs1, targets, mask, inputs2, window], cost, updates=updates)
+    val_fn = function([inputs1, mask, inputs2, window], test_predictions)
+
+`tensor` provides the placeholder constructors the runners use (`T.tensor3`, `T.matrix`, `T.imatrix`,
+`T.ivector`, `T.iscalar`).
+"""
+import numpy as np
+
+from . import layers as L
+from .engine import get_engine
+
+
+class _TensorNamespace(object):
+    @staticmethod
+    def tensor3(name=None, dtype='float32'):
+        return L.Var(name, 3, dtype)
+
+    @staticmethod
+    def matrix(name=None, dtype='float32'):
+        return L.Var(name, 2, dtype)
+
+    @staticmethod
+    def imatrix(name=None):
+        return L.Var(name, 2, 'int32')
+
+    @staticmethod
+    def ivector(name=None):
+        return L.Var(name, 1, 'int32')
+
+    @staticmethod
+    def iscalar(name=None):
+        return L.Var(name, 0, 'int32')
+
+    @staticmethod
+    def mean(x):
+        if isinstance(x, LossExpr) and x.kind == 'categorical_crossentropy_elemwise':
+            return LossExpr('categorical_crossentropy', x.pred, x.targets, None)
+        raise TypeError('T.mean is only defined on categorical_crossentropy(...) here')
+
+
+tensor = _TensorNamespace()
+
+
+class LossExpr(object):
+    def __init__(self, kind, pred, targets, mask):
+        self.kind, self.pred, self.targets, self.mask = kind, pred, targets, mask
+
+
+class UpdateSpec(object):
+    def __init__(self, kind, loss, params, learning_rate=None, lr_map=None, **hp):
+        if not isinstance(loss, LossExpr):
+            raise TypeError('updates need a loss expression')
+        self.kind, self.loss, self.params, self.lr, self.lr_map, self.hp = kind, loss, params, learning_rate, lr_map, hp
+
+
+def _lr_value(lr):
+    return float(lr.get_value()) if hasattr(lr, 'get_value') else float(lr)
+
+
+class shared(object):
+    """Minimal stand-in for a theano shared scalar (learning rates that decay per epoch,
+    `avletters/trimodal.py:436-437`)."""
+
+    def __init__(self, value, name=None):
+        self.value, self.name = np.float32(value), name
+
+    def get_value(self):
+        return self.value
+
+    def set_value(self, v):
+        self.value = np.float32(v)
+
+
+def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_unused_input='raise', **engine_kw):
+    if isinstance(outputs, (list, tuple)):
+        if len(outputs) != 1:
+            raise ValueError('one output expression per function is supported')
+        outputs = outputs[0]
+    if isinstance(outputs, LossExpr):
+        pred = outputs.pred
+    elif isinstance(outputs, L.OutputExpr):
+        pred = outputs
+    else:
+        raise TypeError('outputs must come from layers.get_output(...) or a loss built on it')
+    eng = get_engine(pred.layer, **engine_kw)
+    by_var = {l.input_var: l for l in eng.input_layers}
+    slots = []          # per positional argument: ('input', layer) | ('targets',) | ('mask-only',) | ('window',)
+    for v in inputs:
+        if v in by_var:
+            slots.append(('input', by_var[v]))
+        elif isinstance(outputs, LossExpr) and v is outputs.targets:
+            slots.append(('targets', None))
+        elif isinstance(v, L.Var) and v.ndim == 0:
+            slots.append(('window', None))
+        else:
+            raise ValueError('input %r is not used by the network (unused inputs are an error, as in Theano)' % (v,))
+    need = [l for l in eng.input_layers]
+    have = [s[1] for s in slots if s[0] == 'input']
+    for l in need:
+        if l not in have:
+            raise ValueError('missing input for InputLayer %r' % (l.name,))
+    mask_layer = None
+    if isinstance(outputs, LossExpr) and outputs.mask is not None:
+        mask_layer = by_var.get(outputs.mask)
+        if mask_layer is None:
+            raise ValueError('the loss mask must be the network mask input')
+    is_loss = isinstance(outputs, LossExpr)
+    train = updates is not None
+    loss_name = {'temporal_softmax': 'temporal_softmax',
+                 'categorical_crossentropy': 'categorical_crossentropy'}.get(outputs.kind) if is_loss else None
+    if is_loss and loss_name is None:
+        raise TypeError('wrap categorical_crossentropy(...) in T.mean(...)')
+
+    def fn(*args, **kw):
+        if len(args) != len(slots):
+            raise TypeError('expected %d arguments, got %d' % (len(slots), len(args)))
+        feed, window, y = {}, None, None
+        for (kind, layer), a in zip(slots, args):
+            if kind == 'input':
+                feed[layer] = a
+            elif kind == 'targets':
+                y = a
+            else:
+                window = int(a)
+        dropout_masks = kw.get('dropout_masks')
+        if not is_loss:
+            run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
+            res = eng.read(out)
+            lay = pred.layer
+            if len(lay.output_shape) == 3:
+                res = res.reshape(run.N, run.T, -1)
+            return res
+        mask = feed[mask_layer] if mask_layer is not None else None
+        if not train:
+            run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
+            return eng.loss_only(out, loss_name, y, mask)
+        run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks)
+        eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
+                              count=float(np.asarray(mask).sum()) if (mask is not None and not hasattr(mask, 'is_cuda'))
+                              else None)
+        eng.allreduce_grads()
+        u = updates
+        eng.optim_step(u.kind, _lr_value(u.lr) if u.lr is not None else 0.0, params=u.params, lr_map=u.lr_map, **u.hp)
+        return eng.read_loss()
+
+    fn.engine = eng
+    return fn

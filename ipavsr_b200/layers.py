@@ -38,7 +38,7 @@ class Param(object):
     """
 
     def __init__(self, value, name, tags):
-        self._host = np.ascontiguousarray(value, dtype=np.float32)
+        self._host = np.array(value, dtype=np.float32, order='C')
         self.name = name
         self.tags = set(tags)
         self.shape = self._host.shape
@@ -55,7 +55,7 @@ class Param(object):
         if v.shape != self.shape:
             raise ValueError('mismatch: parameter %s has shape %r but value has shape %r'
                              % (self.name, self.shape, v.shape))
-        self._host = np.ascontiguousarray(v)
+        self._host = np.array(v, dtype=np.float32, order='C')
         if self._binding is not None:
             arena, slot = self._binding
             arena.write(slot, self._host)

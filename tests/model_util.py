@@ -1,0 +1,139 @@
+"""Synthetic small instances of every modelzoo builder + feeds, shared by CPU (wiring) and GPU (parity) tests."""
+import numpy as np
+
+from ipavsr_b200 import layers as L
+from ipavsr_b200 import modelzoo, nonlinearities as nl, init
+from ipavsr_b200.function import tensor as T
+
+
+class FakeDBN(object):
+    """The legacy encoder object form: get_all_layers()[1..4] carry .W/.b (modelzoo/deltanet.py:63-73)."""
+
+    class _Lyr(object):
+        def __init__(self, W, b):
+            self.W, self.b = W, b
+
+    def __init__(self, weights, biases):
+        self._layers = [None] + [FakeDBN._Lyr(w, b) for w, b in zip(weights, biases)]
+
+    def get_all_layers(self):
+        return self._layers
+
+
+def enc_weights(rng, D, shapes=(2000, 1000, 500, 50)):
+    s = [D] + list(shapes)
+    W = [rng.normal(0, 1.0 / np.sqrt(s[i]), (s[i], s[i + 1])).astype('float32') for i in range(len(shapes))]
+    b = [rng.normal(0, 0.1, (s[i + 1],)).astype('float32') for i in range(len(shapes))]
+    return W, b
+
+
+def ae_tuple(rng, D, shapes=(60, 40, 30, 10), acts=('sigmoid', 'rectify', 'tanh', 'linear')):
+    W, b = enc_weights(rng, D, shapes)
+    return W, b, list(shapes), [nl.select_nonlinearity(a) for a in acts]
+
+
+def make_feed(rng, N, T, dims, lens=None):
+    if lens is None:
+        lens = rng.integers(2, T + 1, size=N)
+        lens[0] = T
+    mask = (np.arange(T)[None, :] < np.asarray(lens)[:, None]).astype('uint8')
+    xs = []
+    for D in dims:
+        x = rng.normal(size=(N, T, D)).astype('float32')
+        x *= mask[:, :, None]            # zero padding past len (utils/datagen.py:138-139)
+        xs.append(x)
+    return xs, mask, lens
+
+
+def build(name, rng, C=7, H=12, win=3, fusiontype='sum'):
+    """Returns dict(net, inputs=[(layer-name, array-index)], level='seq'|'frame', dims=[...], extra)."""
+    np.random.seed(int(rng.integers(1 << 30)))
+    v = lambda n: T.tensor3(n)
+    m = T.matrix('mask', dtype='uint8')
+    if name == 'deltanet':
+        D = 40
+        W, b = enc_weights(rng, D)
+        net = modelzoo.deltanet.create_model(FakeDBN(W, b), (None, None, D), v('x'), (None, None), m, H, win, C)
+        return dict(net=net, names=['input'], dims=[D], level='seq')
+    if name == 'deltanet_majority_vote':
+        D = 40
+        net = modelzoo.deltanet_majority_vote.create_model(ae_tuple(rng, D), (None, None, D), v('x'), (None, None), m,
+                                                           H, win, C, init.GlorotUniform(), True, True)
+        return dict(net=net, names=['input'], dims=[D], level='frame')
+    if name == 'deltanet_v1':
+        D = 18
+        net = modelzoo.deltanet_v1.create_model((None, None, D), v('x'), (None, None), m, win, H, C,
+                                                init.GlorotUniform(), False, False)
+        return dict(net=net, names=['input'], dims=[D], level='frame')
+    if name == 'lstm_classifier_baseline':
+        D = 30
+        net = modelzoo.lstm_classifier_baseline.create_model((None, None, D), v('x'), (None, None), m, H, C)
+        return dict(net=net, names=['input'], dims=[D], level='seq')
+    if name == 'adenet_v1':
+        D, Dd = 40, 18
+        W, b = enc_weights(rng, D)
+        net, _ = modelzoo.adenet_v1.create_model(FakeDBN(W, b), (None, None, D), v('x'), (None, None), m,
+                                                 (None, None, Dd), v('dct'), H, win, C)
+        return dict(net=net, names=['input', 'dct'], dims=[D, Dd], level='seq')
+    if name == 'adenet_v2':
+        D, Dd = 40, 18
+        net, fuse = modelzoo.adenet_v2.create_model(ae_tuple(rng, D), (None, None, D), v('x'), (None, None), m,
+                                                    (None, None, Dd), v('dct'), H, win, C, fusiontype,
+                                                    init.GlorotUniform(), True)
+        return dict(net=net, names=['input', 'dct'], dims=[D, Dd], level='frame', fuse=fuse)
+    if name == 'adenet_v3':
+        D, Dd = 40, 18
+        W1, b1 = enc_weights(rng, D)
+        W2, b2 = enc_weights(rng, D)
+        net, fuse = modelzoo.adenet_v3.create_model(FakeDBN(W1, b1), FakeDBN(W2, b2), (None, None, D), v('x'),
+                                                    (None, None), m, (None, None, Dd), v('dct'), (None, None, D),
+                                                    v('diff'), H, win, C, fusiontype)
+        return dict(net=net, names=['raw_im', 'dct', 'diff_im'], dims=[D, Dd, D], level='seq', fuse=fuse)
+    if name == 'adenet_3stream':
+        dims = [40, 24, 32]
+        aes = [ae_tuple(rng, d) for d in dims]
+        net, fuse = modelzoo.adenet_3stream.create_model(aes[0], aes[1], aes[2], (None, None, dims[0]), v('s1'),
+                                                         (None, None, dims[1]), v('s2'), (None, None, dims[2]),
+                                                         v('s3'), (None, None), m, H, win, C, fusiontype)
+        return dict(net=net, names=['s1_im', 's2_im', 's3_im'], dims=dims, level='frame', fuse=fuse)
+    if name == 'adenet_4stream':
+        dims = [40, 24, 32, 20]
+        aes = [ae_tuple(rng, d) for d in dims]
+        net, fuse = modelzoo.adenet_4stream.create_model(aes[0], aes[1], aes[2], aes[3],
+                                                         (None, None, dims[0]), v('s1'), (None, None, dims[1]), v('s2'),
+                                                         (None, None, dims[2]), v('s3'), (None, None, dims[3]), v('s4'),
+                                                         (None, None), m, H, win, C, fusiontype)
+        return dict(net=net, names=['s1_im', 's2_im', 's3_im', 's4_im'], dims=dims, level='frame', fuse=fuse)
+    raise KeyError(name)
+
+
+ALL = ['deltanet', 'deltanet_majority_vote', 'deltanet_v1', 'lstm_classifier_baseline', 'adenet_v1', 'adenet_v2',
+       'adenet_v3', 'adenet_3stream', 'adenet_4stream']
+
+
+def randomize_params(net, rng):
+    """Give every parameter a non-trivial value (biases, peepholes, inits, BN stats, adacoeffs are otherwise 0/1)."""
+    for p in L.get_all_params(net):
+        if p.name and (p.name.endswith('.W') and p.shape[0] > 100):
+            continue                               # keep the scaled encoder weights
+        if p.name and p.name.endswith('inv_std'):
+            p.set_value(rng.uniform(0.5, 1.5, p.shape).astype('float32'))
+        elif p.name and p.name.startswith('adacoeff'):
+            p.set_value(np.float32(rng.uniform(0.5, 1.5)))
+        elif len(p.shape) == 2 and p.shape[0] > 1:
+            p.set_value((p.get_value() + rng.normal(0, 0.05, p.shape)).astype('float32'))
+        else:
+            p.set_value(rng.normal(0, 0.3, p.shape).astype('float32'))
+
+
+def input_layers(net):
+    return {l.name: l for l in L.get_all_layers(net) if isinstance(l, L.InputLayer)}
+
+
+def dropout_masks_for(net, rng, N, T):
+    out = {}
+    for l in L.get_all_layers(net):
+        if isinstance(l, L.DropoutLayer):
+            F = l.output_shape[-1]
+            out[l.name] = (rng.random((N, T, F)) >= l.p).astype('uint8')
+    return out

@@ -1,0 +1,160 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol (no compute), builder wiring and
+parameter order, error conventions, oracle network gradients vs finite differences."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ipavsr_b200 import layers as L, _lib, nonlinearities as nl
+from ipavsr_b200.custom.updates import generate_lr_map
+import model_util as MU
+
+
+def test_library_builds_loads_and_exports_every_header_symbol():
+    lib = _lib.load()
+    names = _lib.header_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _lib._SIGS, 'no ctypes signature for %s' % n
+    assert lib.ipavsr_version() >= 100
+    assert isinstance(lib.ipavsr_launch_count(), int)
+
+
+def test_ctypes_arity_matches_header():
+    text = re.sub(r'/\*.*?\*/', '', open(_lib.HEADER).read(), flags=re.S)
+    for m in re.finditer(r'\b(ipavsr_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;', text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        n = 0 if args in ('', 'void') else args.count(',') + 1
+        assert len(_lib._SIGS[name][1]) == n, name
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _lib.load()
+    rc = lib.ipavsr_gemm(0, 0, 0, -1, 4, 4, None, 4, None, 4, None, 4, None, 0, 0, None, 0, None)
+    assert rc == -1 and b'ipavsr_gemm' in lib.ipavsr_last_error()
+    rc = lib.ipavsr_delta_fwd(None, 4, None, 12, 1, 1, 4, 1, 1, None)
+    assert rc == -1
+
+
+def test_adenet_v2_layer_and_param_order():
+    rng = np.random.default_rng(0)
+    spec = MU.build('adenet_v2', rng, fusiontype='adasum')
+    names = [l.name for l in L.get_all_layers(spec['net'])]
+    assert names == ['input', 'reshape1', 'fc1', 'fc2', 'fc3', 'bottleneck', 'reshape2', 'delta', 'mask', 'lstm_bn',
+                     'dct', 'delta_dct', 'lstm_dct', 'adasum', 'f_lstm_agg', 'b_lstm_agg', 'sum2', 'reshape3',
+                     'softmax', 'output']
+    pn = [p.name for p in L.get_all_params(spec['net'])]
+    assert pn[:8] == ['fc1.W', 'fc1.b', 'fc2.W', 'fc2.b', 'fc3.W', 'fc3.b', 'bottleneck.W', 'bottleneck.b']
+    lstm = ['W_in_to_ingate', 'W_hid_to_ingate', 'b_ingate', 'W_in_to_forgetgate', 'W_hid_to_forgetgate',
+            'b_forgetgate', 'W_in_to_cell', 'W_hid_to_cell', 'b_cell', 'W_in_to_outgate', 'W_hid_to_outgate',
+            'b_outgate']
+    peep = ['W_cell_to_ingate', 'W_cell_to_forgetgate', 'W_cell_to_outgate']
+    init = ['cell_init', 'hid_init']
+    expect = ['lstm_bn.' + n for n in lstm + peep + init] + ['lstm_dct.' + n for n in lstm + peep + init] + \
+             ['adacoeff0', 'adacoeff1'] + ['f_lstm_agg.' + n for n in lstm + init] + \
+             ['b_lstm_agg.' + n for n in lstm + init] + ['softmax.W', 'softmax.b']
+    assert pn[8:] == expect            # the agg BLSTM never gets peepholes (adenet_v2.py:77)
+    assert [p.name for p in L.get_all_params(spec['fuse'], scaling_param=True)] == ['adacoeff0', 'adacoeff1']
+
+
+def test_adenet_v3_order_matches_notebook_print():
+    """avletters/avletters_training.ipynb:462-492 prints this traversal for adenet_v3."""
+    rng = np.random.default_rng(1)
+    spec = MU.build('adenet_v3', rng, H=10)
+    names = [l.name for l in L.get_all_layers(spec['net'])]
+    assert names == ['raw_im', 'reshape1_raw', 'fc1_raw', 'fc2_raw', 'fc3_raw', 'bottleneck_raw', 'reshape2_raw',
+                     'delta_raw', 'dropout_raw', 'mask', 'lstm_raw', 'dct', 'dropout_dct', 'lstm_dct', 'diff_im',
+                     'reshape1_diff', 'fc1_diff', 'fc2_diff', 'fc3_diff', 'bottleneck_diff', 'reshape2_diff',
+                     'delta_diff', 'dropout_diff', 'lstm_diff', 'sum1', 'dropout_agg', 'f_lstm_agg', 'b_lstm_agg',
+                     'sum2', 'slice1', 'output']
+    lstm_raw = [l for l in L.get_all_layers(spec['net']) if l.name == 'lstm_raw'][0]
+    assert lstm_raw.num_units == 20 and lstm_raw.peepholes          # int(lstm_size/(1-0.5)), Lasagne default peepholes
+    agg = [l for l in L.get_all_layers(spec['net']) if l.name == 'f_lstm_agg'][0]
+    assert agg.num_units == 20 and agg.peepholes
+
+
+@pytest.mark.parametrize('name', MU.ALL)
+def test_every_builder_builds(name):
+    rng = np.random.default_rng(2)
+    spec = MU.build(name, rng, fusiontype='concat' if name.startswith('adenet_') and name != 'adenet_v1' else 'sum')
+    net = spec['net']
+    shapes = net.output_shape
+    assert shapes[-1] == 7
+    assert (len(shapes) == 3) == (spec['level'] == 'frame')
+    vals = L.get_all_param_values(net)
+    L.set_all_param_values(net, vals)
+    with pytest.raises(ValueError):
+        L.set_all_param_values(net, vals[:-1])
+
+
+def test_shapes_and_quirks():
+    rng = np.random.default_rng(3)
+    s = MU.build('adenet_v1', rng, H=8)
+    byname = {l.name: l for l in L.get_all_layers(s['net'])}
+    assert byname['concat'].output_shape[-1] == 150 + 18
+    assert byname['f_lstm1'].peepholes and byname['f_lstm2'].num_units == 16
+    assert [p.name for p in byname['batchnorm1'].params] == ['batchnorm1.beta', 'batchnorm1.gamma', 'batchnorm1.mean',
+                                                             'batchnorm1.inv_std']
+    assert [p.name for p in byname['batchnorm1'].get_params(trainable=True)] == ['batchnorm1.beta', 'batchnorm1.gamma']
+    s2 = MU.build('adenet_v2', rng, fusiontype='concat')
+    b2 = {l.name: l for l in L.get_all_layers(s2['net'])}
+    assert b2['delta_dct'].output_shape[-1] == 54 and b2['f_lstm_agg'].num_inputs == 24 and not b2['f_lstm_agg'].peepholes
+    s4 = MU.build('adenet_4stream', rng, fusiontype='concat')
+    assert {l.name: l for l in L.get_all_layers(s4['net'])}['f_lstm_agg'].num_inputs == 48
+    with pytest.raises(ValueError):
+        MU.build('adenet_v2', rng, fusiontype='bogus')
+    with pytest.raises(KeyError):
+        nl.select_nonlinearity('nope')
+
+
+def test_generate_lr_map_prefix_rule():
+    rng = np.random.default_rng(4)
+    s = MU.build('adenet_v2', rng, fusiontype='adasum')
+    params = L.get_all_params(s['net'], trainable=True)
+    m = generate_lr_map(params, {'fc1': 0.5, 'lstm_bn': 0.25, 'adacoeff': 0.125}, 1.0)
+    byname = {p.name: v for p, v in m.items()}
+    assert byname['fc1.W'] == 0.5 and byname['fc2.W'] == 1.0 and byname['lstm_bn.cell_init'] == 0.25
+    assert byname['adacoeff0'] == 0.125          # 'adacoeff0'[:rfind('.')] == 'adacoeff' (custom/updates.py:27)
+
+
+@pytest.mark.parametrize('name', ['adenet_v2', 'adenet_v1', 'adenet_v3'])
+def test_oracle_network_gradients_vs_finite_differences(name):
+    from oracle.net import OracleNet
+    rng = np.random.default_rng(7)
+    spec = MU.build(name, rng, C=5, H=6, win=2, fusiontype='adasum')
+    net = spec['net']
+    MU.randomize_params(net, rng)
+    N, T = 4, 6
+    xs, mask, lens = MU.make_feed(rng, N, T, spec['dims'])
+    feed = dict(zip(spec['names'], xs))
+    feed['mask'] = mask
+    y1 = rng.integers(0, 5, size=N)
+    level = spec['level']
+    y = y1 if level == 'seq' else np.repeat(y1[:, None], T, 1)
+    loss_name = 'categorical_crossentropy' if level == 'seq' else 'temporal_softmax'
+    dm = MU.dropout_masks_for(net, rng, N, T)
+    o = OracleNet(net, np.float64)
+    f = lambda: float(o.loss_and_grads(feed, 2, y, mask, loss_name, False, dm, update_bn=False)[0])
+    _, _, grads = o.loss_and_grads(feed, 2, y, mask, loss_name, False, dm, update_bn=False)
+    params = L.get_all_params(net, trainable=True)
+    eps = 1e-5
+    checked = 0
+    for p, g in zip(params, grads):
+        base = p.get_value().astype(np.float64)
+        flat = max(int(np.prod(p.shape)), 1)
+        idx = np.unravel_index(int(rng.integers(0, flat)), p.shape) if p.shape else ()
+        vals = {}
+        for sgn in (1, -1):
+            v = base.copy()
+            v[idx] = v[idx] + sgn * eps
+            p.get_value = (lambda vv: (lambda: vv))(v)        # float64 value straight into the float64 oracle
+            vals[sgn] = f()
+            del p.get_value
+        num = (vals[1] - vals[-1]) / (2 * eps)
+        ana = float(g[idx])
+        assert abs(num - ana) < 1e-6 + 1e-4 * abs(num), (p.name, idx, num, ana)
+        checked += 1
+    assert checked == len(params)
