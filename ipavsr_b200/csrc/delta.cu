@@ -10,8 +10,9 @@
 // (utterance, feature, 4-frame run) and slides a register window of 2*Theta+4 frames over it (window loads are
 // bank-conflict-free: lanes walk the feature axis), writes d back to shared memory, repeats for a, then the CTA
 // streams the [x|d|a] rows out coalesced.  Algorithmic traffic 16*F bytes/frame (read 4F, write 12F): HBM-bound.
-// EXACT=true keeps the reference's float64 intermediates (DFMA with the exact reciprocal, float32 round per
-// theta); EXACT=false is a plain float32 FMA chain (few-ulp deviation, stated in DESIGN.md).
+// EXACT=true reproduces the reference's float64 operation sequence bit for bit (correctly rounded quotient, float64
+// add, float32 round per theta; FP64-pipe bound); EXACT=false is a plain float32 FMA chain (few-ulp deviation, stated
+// in DESIGN.md; HBM bound).
 #include "common.cuh"
 
 namespace ipavsr {
@@ -22,9 +23,21 @@ constexpr int DELTA_RUN = 4;
 template <bool EXACT>
 __device__ __forceinline__ float delta_step(float acc, float diff, int th) {
   if (EXACT) {
-    // round32( acc + diff/(2 th) ) with a float64 intermediate (utils/signal.py:19-21)
-    double r = 1.0 / (2.0 * (double)th);
-    return (float)fma((double)diff, r, (double)acc);
+    // The reference evaluates, in float64:  term = (theta*diff) / (2*theta*theta)  [= RN53(diff / (2 theta)), the
+    // numerator is exact],  s = RN53(acc + term),  acc = RN24(s)   (utils/signal.py:19-21).  Exact float32 ties of s
+    // are common (whenever 2*theta divides diff's mantissa), so the quotient has to be the correctly rounded one:
+    // for a power-of-two theta the product diff * (1/(2 theta)) is exact; otherwise one Markstein correction step
+    // (q = d*r; rem = fma(-q, c, d) exact; q' = fma(rem, r, q)) gives the correctly rounded quotient for these small
+    // integer divisors c.
+    const double c = 2.0 * (double)th;
+    const double r = 1.0 / c;
+    const double d = (double)diff;
+    double q = d * r;
+    if ((th & (th - 1)) != 0) {
+      const double rem = fma(-q, c, d);
+      q = fma(rem, r, q);
+    }
+    return (float)((double)acc + q);
   } else {
     return fmaf(diff, 1.0f / (2.0f * (float)th), acc);
   }

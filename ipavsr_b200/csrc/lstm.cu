@@ -588,7 +588,7 @@ int ipavsr_lstm_bwd(const float* dout, const float* w_hid, const float* peep, co
   float* dc_fin = base + 2 * NH;
   float* dh_fin = base + 3 * NH;
   float* ppart = base + 8 * NH;       // [3,N,H]
-  float* wT = ppart + 3 * NH;         // [4H][ldt]
+  float* wT = ws + ((4 * NH + 8 * NH + 3 * NH + 3) / 4) * 4;   // [4H][ldt], 16-byte aligned for float4 loads
   const int cs = (H + LU - 1) / LU;
   if (impl == 0 && cs > 16) impl = 1;
   const int t_first = backwards ? T - 1 : 0;   // the first *processed* step

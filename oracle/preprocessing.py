@@ -30,12 +30,14 @@ def featurewise_normalize_sequence(x):
 
 
 def sequencewise_mean_image_subtraction(x, seqlens):
-    """`utils/preprocessing.py:260-277`: remove each utterance's mean frame."""
+    """`utils/preprocessing.py:260-277`: remove each utterance's mean frame.  All arithmetic stays in the input dtype
+    (float32), as under the reference's NumPy 1.x value-based casting (`float32_array / integer_scalar`)."""
     out = np.zeros(x.shape, x.dtype)
     start = 0
     for l in seqlens:
+        l = int(l)
         seq = x[start:start + l]
-        out[start:start + l] = seq - np.sum(seq, 0, x.dtype) / l
+        out[start:start + l] = seq - np.sum(seq, 0, x.dtype) / x.dtype.type(l)
         start += l
     return out
 
@@ -73,6 +75,7 @@ def compute_diff_images(X, vidlenvec):
     out = np.zeros(X.shape, X.dtype)
     start = 0
     for l in vidlenvec:
+        l = int(l)
         seq = X[start:start + l]
         d = np.diff(seq, 1, 0)
         out[start] = d[0]

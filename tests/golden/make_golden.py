@@ -33,7 +33,11 @@ from utils import preprocessing as ref                  # noqa: E402
 def main():
     rng = np.random.default_rng(20261017)
     out = {}
-    lens = np.array([12, 9, 20, 15, 11], dtype=np.int64)
+    # utterance lengths are passed as a list of Python ints: under NumPy >= 2 (NEP 50) `float32_array / np.int64`
+    # promotes to float64, whereas the reference's NumPy 1.x era value-based casting keeps float32; a Python int
+    # divisor reproduces the era's float32 arithmetic in `sequencewise_mean_image_subtraction` (:273)
+    lens_list = [12, 9, 20, 15, 11]
+    lens = np.array(lens_list, dtype=np.int64)
     frames = int(lens.sum())
     X = rng.normal(3.0, 2.0, size=(frames, 48)).astype(np.float32)
     out['lens'] = lens
@@ -41,12 +45,12 @@ def main():
     out['normalize_input'] = ref.normalize_input(X.copy())
     n, mean, std = ref.featurewise_normalize_sequence(X.copy())
     out['featurewise_norm'], out['featurewise_mean'], out['featurewise_std'] = n, mean, std
-    out['seq_mean_sub'] = ref.sequencewise_mean_image_subtraction(X.copy(), lens)
-    out['diff_images'] = ref.compute_diff_images(X.copy(), lens)
+    out['seq_mean_sub'] = ref.sequencewise_mean_image_subtraction(X.copy(), lens_list)
+    out['diff_images'] = ref.compute_diff_images(X.copy(), lens_list)
     Xd = rng.normal(size=(frames, 30)).astype(np.float32)
     out['Xd'] = Xd
-    out['concat_deltas_w9'] = ref.concat_first_second_deltas(Xd.copy(), lens, 9)
-    out['concat_deltas_w5'] = ref.concat_first_second_deltas(Xd.copy(), lens, 5)
+    out['concat_deltas_w9'] = ref.concat_first_second_deltas(Xd.copy(), lens_list, 9)
+    out['concat_deltas_w5'] = ref.concat_first_second_deltas(Xd.copy(), lens_list, 5)
     a = np.array([[1, 1, 1, 1, 1, 1, 1, 1, 10], [2, 2, 2, 2, 2, 2, 2, 2, 20],
                   [3, 3, 3, 3, 3, 3, 3, 3, 30], [4, 4, 4, 4, 4, 4, 4, 4, 40]])       # utils/preprocessing.py:12
     out['test_delta_in'] = a
