@@ -1,11 +1,486 @@
-// placeholder until the tcgen05 kernel lands (next commit): report "unsupported" so ipavsr_gemm uses FP32.
+// Tensor-core GEMM for sm_100a: TMA-fed tcgen05.mma (kind::tf32) with the accumulator in TMEM and a fused
+// bias + nonlinearity epilogue.  Modes: IPAVSR_GEMM_TF32 (one MMA per product) and IPAVSR_GEMM_TF32X3 — the fp32
+// parity mode: every operand is split a = hi + lo with hi, lo exactly representable in tf32 and the product is
+// accumulated as lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22 relative).
+//
+// Replaces the cuBLAS/BLAS sgemm behind Theano's T.dot in the DBNF encoder (reference
+// modelzoo/pretrained_encoder.py:4-9), the hoisted LSTM input projections and all their dgrad/wgrad products.
+//
+// Structure (one CTA per 128 x BN output tile, optional split-K over gridDim.z):
+//   warp 0  TMA producer   cp.async.bulk.tensor.2d global -> 128B-swizzled shared tiles, mbarrier complete_tx
+//   warp 1  MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8),
+//                          tcgen05.commit releases the shared stage / signals the epilogue
+//   warp 2  TMEM allocator tcgen05.alloc / dealloc of BN columns
+//   warps 4-7 epilogue     tcgen05.ld 32x32b (one TMEM lane = one output row per thread), bias + activation,
+//                          vectorised global stores (or float atomics for split-K)
+// Operand layouts: a K-major operand (reduction dim contiguous) is one TMA box of [rows x 32 floats]; an MN-major
+// operand (stored transposed: A as [K,M] for wgrad, B as [K,N] for the forward x*W) is BLOCK/32 boxes of
+// [32 k-rows x 32 floats] (TMA swizzle 128B_ATOM_32B) and is consumed through MN-major UMMA descriptors
+// (SWIZZLE_128B_BASE32B) — no transposed copies are made.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace ipavsr {
-bool gemm_tc_supported(int, int, int, int, int, const float*, int, const float*, int, const float*, int) { return false; }
-uint64_t gemm_tc_workspace_bytes(int, int, int, int, int, int) { return 0; }
-int gemm_tc(int, int, int, int, int, int, const float*, int, const float*, int, float*, int, const float*, int, int,
-            void*, uint64_t, cudaStream_t) {
-  set_error("gemm_tc: not built");
-  return IPAVSR_ERR_UNSUPPORTED;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // floats per stage along K (one 128-byte swizzle row)
+constexpr int TC_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory matrix descriptor (version 1).  Address/offset fields in 16-byte units.
+// layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B — the only layout the tensor core accepts
+// for MN-major 32-bit (tf32) operands; its TMA counterpart is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+struct TcParams {
+  int M, N, K;
+  float* C;
+  int ldc;
+  const float* bias;
+  int act;
+  int accumulate;
+  int kb_per_split;   // k-blocks (of TC_BK) per split
+  int splits;
+};
+
+template <int BN, bool A_MN, bool B_MN, int NPROD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+               const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, TcParams p) {
+  constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
+  constexpr int B_BYTES = BN * TC_BK * 4;
+  constexpr int NOPER = (NPROD == 3) ? 2 : 1;         // hi (+ lo) copies of each operand
+  constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
+  constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int num_kb_total = (p.K + TC_BK - 1) / TC_BK;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = max(kb_end - kb_begin, 0);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                 "r"((uint32_t)BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+      uint8_t* sB = sA + NOPER * A_BYTES;
+      mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+      const int k0 = (kb_begin + kb) * TC_BK;
+#pragma unroll
+      for (int o = 0; o < NOPER; ++o) {
+        const CUtensorMap* ma = o == 0 ? &mapA : &mapAlo;
+        const CUtensorMap* mb = o == 0 ? &mapB : &mapBlo;
+        if (!A_MN) {
+          tma_load_2d(sA + o * A_BYTES, ma, &full_bar[stage], k0, m0);                 // box {32 k, 128 rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j)                                         // boxes {32 m, 32 k-rows}
+            tma_load_2d(sA + o * A_BYTES + j * 4096, ma, &full_bar[stage], m0 + 32 * j, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB + o * B_BYTES, mb, &full_bar[stage], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d(sB + o * B_BYTES + j * 4096, mb, &full_bar[stage], n0 + 32 * j, k0);
+        }
+      }
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+      const uint32_t sB = sA + NOPER * A_BYTES;
+#pragma unroll
+      for (int k = 0; k < TC_BK / 8; ++k) {
+        // K-major (SWIZZLE_128B): advance 32 bytes inside the swizzled 128-byte row; SBO = 1024 (8 rows).
+        // MN-major (SWIZZLE_128B_BASE32B, atoms of 4 k-rows x 128 bytes): advance 8 k-rows (1024 bytes);
+        // SBO = 512 (next 4-row atom along K), LBO = 4096 (next 32-wide chunk along M/N = next TMA box).
+        const uint32_t a_off = A_MN ? k * 1024 : k * 32;
+        const uint32_t b_off = B_MN ? k * 1024 : k * 32;
+        const uint32_t a_lbo = A_MN ? 4096 : 16, b_lbo = B_MN ? 4096 : 16;
+        const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
+        const uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
+        const uint64_t a_hi = make_smem_desc(sA + a_off, a_lbo, a_sbo, a_lt);
+        const uint64_t b_hi = make_smem_desc(sB + b_off, b_lbo, b_sbo, b_lt);
+        const uint32_t first = (kb | k) == 0 ? 0u : 1u;
+        if (NPROD == 3) {
+          const uint64_t a_lo = make_smem_desc(sA + A_BYTES + a_off, a_lbo, a_sbo, a_lt);
+          const uint64_t b_lo = make_smem_desc(sB + B_BYTES + b_off, b_lbo, b_sbo, b_lt);
+          tcgen05_mma_tf32(tmem_base, a_lo, b_hi, idesc, first);
+          tcgen05_mma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+          tcgen05_mma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+        } else {
+          tcgen05_mma_tf32(tmem_base, a_hi, b_hi, idesc, first);
+        }
+      }
+      tcgen05_commit(&empty_bar[stage]);          // frees this shared stage once the MMAs above have read it
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    tcgen05_commit(&accum_bar);                   // accumulator complete
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int row = m0 + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(&accum_bar, 0);
+      tcgen05_fence_after();
+    }
+    const bool split = p.splits > 1;
+    const bool vec = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;                   // warp-uniform
+      float v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (row < p.M) {
+        float* cp = p.C + (size_t)row * p.ldc + n0 + c0;
+        if (split) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < p.N) {
+              float add = v[j];
+              if (p.bias != nullptr && blockIdx.z == 0) add += __ldg(p.bias + n0 + c0 + j);
+              atomicAdd(cp + j, add);
+            }
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const int col = n0 + c0 + j4;
+            if (col >= p.N) break;
+            if (vec && col + 3 < p.N) {
+              float4 o = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+              if (p.accumulate) {
+                float4 old = *reinterpret_cast<const float4*>(cp + j4);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              if (p.bias != nullptr) {
+                o.x += __ldg(p.bias + col); o.y += __ldg(p.bias + col + 1);
+                o.z += __ldg(p.bias + col + 2); o.w += __ldg(p.bias + col + 3);
+              }
+              o.x = act_fwd(o.x, p.act); o.y = act_fwd(o.y, p.act); o.z = act_fwd(o.z, p.act); o.w = act_fwd(o.w, p.act);
+              *reinterpret_cast<float4*>(cp + j4) = o;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col + j < p.N) {
+                  float o = v[j4 + j];
+                  if (p.accumulate) o += cp[j4 + j];
+                  if (p.bias != nullptr) o += __ldg(p.bias + col + j);
+                  cp[j4 + j] = act_fwd(o, p.act);
+                }
+            }
+          }
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): both exactly representable in tf32
+__global__ void tf32_split_rna_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                      size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    float in[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[j]));
+      h[j] = __uint_as_float(hb);
+      float rem = in[j] - h[j];
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+      l[j] = __uint_as_float(lb);
+    }
+    reinterpret_cast<float4*>(hi)[i] = make_float4(h[0], h[1], h[2], h[3]);
+    reinterpret_cast<float4*>(lo)[i] = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D row-major fp32 tensor [outer][inner] with row stride ld floats; box {box_inner, box_outer}; 128B swizzle
+static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+    return IPAVSR_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed with %d (inner %llu outer %llu ld %llu)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+    return IPAVSR_ERR_CUDA;
+  }
+  return IPAVSR_OK;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                       const float* C, int ldc) {
+  (void)transA; (void)transB; (void)C; (void)ldc;
+  if (!aligned16(A) || !aligned16(B) || lda % 4 != 0 || ldb % 4 != 0) return false;
+  if (K < 16 || M < 1 || N < 8) return false;
+  // tiny products are launch-latency bound either way; the FP32 kernel handles them exactly
+  if ((double)M * N * K < 4.0e6) return false;
+  return true;
+}
+
+static size_t operand_floats(int trans_rows, int ld) { return up((size_t)trans_rows * ld, 4); }
+
+uint64_t gemm_tc_workspace_bytes(int mode, int transA, int transB, int M, int N, int K) {
+  if (mode != IPAVSR_GEMM_TF32X3) return 0;
+  // hi/lo copies of both operands, sized with padded leading dimensions (ld <= extent rounded up to 4 ... the caller's
+  // ld can be larger; ipavsr_gemm re-checks against the actual ld)
+  size_t a = (size_t)(transA ? K : M) * up(transA ? M : K, 4) + 64;
+  size_t b = (size_t)(transB ? N : K) * up(transB ? K : N, 4) + 64;
+  return 2 * (a + b) * sizeof(float) * 2;   // x2 head-room for leading dimensions up to twice the logical width
+}
+
+template <int BN, bool A_MN, bool B_MN, int NPROD>
+static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo,
+                     TcParams p, cudaStream_t st) {
+  constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
+  constexpr int NOPER = (NPROD == 3) ? 2 : 1;
+  constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
+  constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD>;
+  IPAVSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
+  kern<<<grid, TC_THREADS, smem, st>>>(mA, mAlo, mB, mBlo, p);
+  IPAVSR_LAUNCH_CHECK();
+  return IPAVSR_OK;
+}
+
+template <int BN, int NPROD>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
+                          const CUtensorMap& mBlo, TcParams p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD>(mA, mAlo, mB, mBlo, p, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD>(mA, mAlo, mB, mBlo, p, st);
+  return launch_tc<BN, true, true, NPROD>(mA, mAlo, mB, mBlo, p, st);
+}
+
+int gemm_tc(int mode, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+            float* C, int ldc, const float* bias, int act, int accumulate, void* ws, uint64_t ws_bytes,
+            cudaStream_t st) {
+  const bool x3 = mode == IPAVSR_GEMM_TF32X3;
+  const bool a_mn = transA != 0;     // A stored [K,M]: M contiguous
+  const bool b_mn = transB == 0;     // B stored [K,N]: N contiguous
+  const float *Ahi = A, *Alo = A, *Bhi = B, *Blo = B;
+  if (x3) {
+    const size_t a_n = operand_floats(transA ? K : M, lda), b_n = operand_floats(transB ? N : K, ldb);
+    const size_t need = (2 * a_n + 2 * b_n + 16) * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) {
+      set_error("gemm_tc: workspace too small (%llu < %llu bytes)", (unsigned long long)ws_bytes,
+                (unsigned long long)need);
+      return IPAVSR_ERR_ARG;
+    }
+    float* w = reinterpret_cast<float*>(ws);
+    float *ah = w, *al = w + a_n, *bh = w + 2 * a_n, *bl = w + 2 * a_n + b_n;
+    const int cap = sm_count() * 8;
+    size_t a4 = a_n / 4, b4 = b_n / 4;
+    tf32_split_rna_kernel<<<(int)((a4 + 255) / 256 < (size_t)cap ? (a4 + 255) / 256 : cap), 256, 0, st>>>(A, ah, al, a4);
+    IPAVSR_LAUNCH_CHECK();
+    tf32_split_rna_kernel<<<(int)((b4 + 255) / 256 < (size_t)cap ? (b4 + 255) / 256 : cap), 256, 0, st>>>(B, bh, bl, b4);
+    IPAVSR_LAUNCH_CHECK();
+    Ahi = ah; Alo = al; Bhi = bh; Blo = bl;
+  }
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap mA, mAlo, mB, mBlo;
+  int rc;
+  // A: K-major -> tensor [M][K], box {32, 128};  MN-major -> tensor [K][M], box {32, 32}
+  if (!a_mn) {
+    if ((rc = make_map(&mA, Ahi, K, M, lda, TC_BK, TC_BM, false))) return rc;
+    if ((rc = make_map(&mAlo, Alo, K, M, lda, TC_BK, TC_BM, false))) return rc;
+  } else {
+    if ((rc = make_map(&mA, Ahi, M, K, lda, 32, TC_BK, true))) return rc;
+    if ((rc = make_map(&mAlo, Alo, M, K, lda, 32, TC_BK, true))) return rc;
+  }
+  if (!b_mn) {
+    if ((rc = make_map(&mB, Bhi, K, N, ldb, TC_BK, BN, false))) return rc;
+    if ((rc = make_map(&mBlo, Blo, K, N, ldb, TC_BK, BN, false))) return rc;
+  } else {
+    if ((rc = make_map(&mB, Bhi, N, K, ldb, 32, TC_BK, true))) return rc;
+    if ((rc = make_map(&mBlo, Blo, N, K, ldb, 32, TC_BK, true))) return rc;
+  }
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  int splits = 1;
+  if (act == IPAVSR_ACT_LINEAR && tiles * 2 <= sm_count() && num_kb >= 32) {
+    splits = sm_count() / tiles;
+    if (splits > num_kb / 8) splits = num_kb / 8;
+    if (splits > 32) splits = 32;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.splits = splits;
+  if (splits > 1 && !accumulate)
+    IPAVSR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+#define IPAVSR_TC_DISPATCH(BNV)                                                                       \
+  return x3 ? dispatch_major<BNV, 3>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)                           \
+            : dispatch_major<BNV, 1>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)
+  if (BN == 64) { IPAVSR_TC_DISPATCH(64); }
+  if (BN == 128) { IPAVSR_TC_DISPATCH(128); }
+  IPAVSR_TC_DISPATCH(256);
+#undef IPAVSR_TC_DISPATCH
+}
+
 }  // namespace ipavsr

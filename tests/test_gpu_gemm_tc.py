@@ -1,0 +1,67 @@
+"""tcgen05 GEMM modes (TF32 single pass, 3xTF32 fp32-parity) against a float64 product, all operand layouts."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops
+import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 256, 64), (1040, 2000, 1200), (300, 1000, 152), (2048, 52, 500), (1200, 2000, 4096),
+          (252, 1000, 1040), (1040, 250, 1000), (129, 130, 200), (4096, 2000, 1200)]
+
+
+def _run(mode, ta, tb, M, N, K, act=0, acc=0, use_bias=False, seed=0):
+    rng = np.random.default_rng(seed + M + N + K)
+    lda = ((M if ta else K) + 3) // 4 * 4
+    ldb = ((K if tb else N) + 3) // 4 * 4
+    ldc = (N + 3) // 4 * 4
+    A = np.zeros((K if ta else M, lda), 'float32')
+    B = np.zeros((N if tb else K, ldb), 'float32')
+    A[:, :(M if ta else K)] = rng.normal(size=(K if ta else M, M if ta else K))
+    B[:, :(K if tb else N)] = rng.normal(size=(N if tb else K, K if tb else N))
+    bias = rng.normal(size=(N,)).astype('float32')
+    C0 = np.zeros((M, ldc), 'float32')
+    C0[:, :N] = rng.normal(size=(M, N))
+    Aop = (A[:, :M].T if ta else A[:, :K]).astype(np.float64)
+    Bop = (B[:, :K].T if tb else B[:, :N]).astype(np.float64)
+    ref = Aop @ Bop + (C0[:, :N] if acc else 0) + (bias if use_bias else 0)
+    want = ops.act_fwd(ref, act)
+    dA, dB, db, dC = G.dev(A), G.dev(B), G.dev(bias), G.dev(C0)
+    need = G.lib().ipavsr_gemm_workspace_bytes(mode, ta, tb, M, N, K)
+    ws = G.zeros((max(need // 4, 4),))
+    G.call('ipavsr_gemm', mode, ta, tb, M, N, K, dA.data_ptr(), lda, dB.data_ptr(), ldb, dC.data_ptr(), ldc,
+           db.data_ptr() if use_bias else None, act, acc, ws.data_ptr(), int(need), G.stream())
+    got = G.host(dC)
+    if ldc > N:
+        np.testing.assert_array_equal(got[:, N:], C0[:, N:])          # padding columns untouched
+    scale = np.abs(Aop).max() * np.abs(Bop).max() * np.sqrt(K)
+    return np.abs(got[:, :N] - want).max() / max(scale, 1e-30) if act == 0 else G.relerr(got[:, :N], want)
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('ta,tb', [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_tf32x3_matches_fp32_parity(M, N, K, ta, tb):
+    err = _run(1, ta, tb, M, N, K)
+    assert err < 2e-6, err            # 3xTF32: fp32-class accuracy (plain TF32 would be ~3e-4 here)
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES[:5])
+@pytest.mark.parametrize('ta,tb', [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_tf32_single_pass(M, N, K, ta, tb):
+    err = _run(2, ta, tb, M, N, K)
+    assert err < 1e-3, err            # stated tolerance of the TF32 mode (10-bit mantissa operands)
+
+
+@pytest.mark.parametrize('act,acc,use_bias', [(1, 0, True), (2, 1, True), (0, 1, False), (3, 0, True)])
+def test_epilogue_variants(act, acc, use_bias):
+    for mode, tol in ((1, 2e-5), (2, 5e-3)):
+        err = _run(mode, 0, 0, 1040, 2000, 1200, act, acc, use_bias)
+        assert err < tol, (mode, err)
+
+
+def test_three_term_split_beats_single_pass():
+    e3 = _run(1, 0, 0, 1040, 1000, 2000)
+    e1 = _run(2, 0, 0, 1040, 1000, 2000)
+    assert e3 < e1 / 50, (e3, e1)
