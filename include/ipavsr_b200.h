@@ -69,6 +69,17 @@ int ipavsr_gemm(int mode, int transA, int transB, int M, int N, int K,
                 const float* bias, int act, int accumulate,
                 void* workspace, uint64_t workspace_bytes, void* stream);
 uint64_t ipavsr_gemm_workspace_bytes(int mode, int transA, int transB, int M, int N, int K);
+/* 1 if the tensor-core kernels take this product (16-byte aligned operands, ld % 4 == 0, K >= 16, N >= 8 and at
+ * least 4 MFLOP-ish of work); ipavsr_gemm computes everything else with the FP32 kernel. */
+int ipavsr_gemm_tc_supported(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
+                             int ldb, const float* C, int ldc);
+/* hi = rna_tf32(x), lo = rna_tf32(x - hi): the operand split of the 3xTF32 mode, done once per tensor and reused. */
+int ipavsr_tf32_split_rna(const float* x, float* hi, float* lo, uint64_t n, void* stream);
+/* 3xTF32 product on operands that are already split (same layout/ld for the hi and lo halves).  C_hi/C_lo (optional,
+ * same ldc as C) receive the split of the result so that a following GEMM needs no split pass. */
+int ipavsr_gemm_tf32x3_presplit(int transA, int transB, int M, int N, int K, const float* A_hi, const float* A_lo,
+                                int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
+                                const float* bias, int act, int accumulate, float* C_hi, float* C_lo, void* stream);
 
 /* dZ = dY * act'(Y)  and  db[N] (+)= column sums of dZ   (backward of DenseLayer's nonlinearity and bias).
  * dZ may alias dY.  db may be NULL. */

@@ -26,6 +26,9 @@ _SIGS = {
     'ipavsr_device_info': (I, [P, P, P, P]),
     'ipavsr_gemm': (I, [I, I, I, I, I, I, P, I, P, I, P, I, P, I, I, P, U64, P]),
     'ipavsr_gemm_workspace_bytes': (U64, [I, I, I, I, I, I]),
+    'ipavsr_gemm_tc_supported': (I, [I, I, I, I, I, P, I, P, I, P, I]),
+    'ipavsr_tf32_split_rna': (I, [P, P, P, U64, P]),
+    'ipavsr_gemm_tf32x3_presplit': (I, [I, I, I, I, I, P, P, I, P, P, I, P, I, P, I, I, P, P, P]),
     'ipavsr_dense_bwd_prep': (I, [P, I, P, I, P, I, P, I, I, I, I, P]),
     'ipavsr_colsum': (I, [P, I, P, I, I, I, P]),
     'ipavsr_delta_fwd': (I, [P, I, P, I, I, I, I, I, I, P]),

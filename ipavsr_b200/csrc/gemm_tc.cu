@@ -91,6 +91,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// a = hi + lo (+ ~2^-22 |a|) with hi and lo exactly representable in tf32
+__device__ __forceinline__ void tf32_hi_lo(float a, float& hi, float& lo) {
+  uint32_t hb, lb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+  hi = __uint_as_float(hb);
+  float rem = a - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+  lo = __uint_as_float(lb);
+}
+
 // UMMA shared-memory matrix descriptor (version 1).  Address/offset fields in 16-byte units.
 // layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B — the only layout the tensor core accepts
 // for MN-major 32-bit (tf32) operands; its TMA counterpart is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
@@ -120,6 +130,8 @@ struct TcParams {
   int accumulate;
   int kb_per_split;   // k-blocks (of TC_BK) per split
   int splits;
+  float* Chi;         // optional: rna_tf32(C) and rna_tf32(C - Chi), same ldc (operands of a following 3xTF32 GEMM)
+  float* Clo;
 };
 
 template <int BN, bool A_MN, bool B_MN, int NPROD>
@@ -132,6 +144,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
   constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
   static_assert(STAGES >= 2, "need at least a double buffer");
+  // TMEM accumulators.  The tensor core adds into its fp32 accumulator with truncation, so the error grows with the
+  // number of accumulations into one accumulator.  In the 3xTF32 mode the tiny cross terms (lo*hi + hi*lo) get their
+  // own accumulator and the hi*hi terms are spread round-robin (by k-block) over NMAIN accumulators; the epilogue sums
+  // them in registers with round-to-nearest.
+  constexpr int TMEM_COLS = (NPROD == 3) ? 512 : BN;
+  constexpr int NMAIN = (NPROD == 3) ? (512 / BN - 1) : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -155,7 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                 "r"((uint32_t)BN)
+                 "r"((uint32_t)TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -221,9 +239,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (NPROD == 3) {
           const uint64_t a_lo = make_smem_desc(sA + A_BYTES + a_off, a_lbo, a_sbo, a_lt);
           const uint64_t b_lo = make_smem_desc(sB + B_BYTES + b_off, b_lbo, b_sbo, b_lt);
-          tcgen05_mma_tf32(tmem_base, a_lo, b_hi, idesc, first);
-          tcgen05_mma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-          tcgen05_mma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          const uint32_t t_cross = tmem_base + (uint32_t)(NMAIN * BN);
+          const uint32_t t_main = tmem_base + (uint32_t)((kb % NMAIN) * BN);
+          const uint32_t main_acc = (kb < NMAIN && k == 0) ? 0u : 1u;
+          tcgen05_mma_tf32(t_cross, a_lo, b_hi, idesc, first);
+          tcgen05_mma_tf32(t_cross, a_hi, b_lo, idesc, 1u);
+          tcgen05_mma_tf32(t_main, a_hi, b_hi, idesc, main_acc);
         } else {
           tcgen05_mma_tf32(tmem_base, a_hi, b_hi, idesc, first);
         }
@@ -247,7 +268,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (n0 + c0 >= p.N) break;                   // warp-uniform
       float v[32];
       if (num_kb > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        if (NPROD == 3) {
+          tmem_ld32(lane_base + (uint32_t)(NMAIN * BN), v);                 // cross terms first (smallest)
+          const int used = num_kb < NMAIN ? num_kb : NMAIN;
+#pragma unroll 1
+          for (int a = 0; a < used; ++a) {
+            float u[32];
+            tmem_ld32(lane_base + (uint32_t)(a * BN), u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
+        } else {
+          tmem_ld32(lane_base, v);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -279,6 +313,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               }
               o.x = act_fwd(o.x, p.act); o.y = act_fwd(o.y, p.act); o.z = act_fwd(o.z, p.act); o.w = act_fwd(o.w, p.act);
               *reinterpret_cast<float4*>(cp + j4) = o;
+              if (p.Chi != nullptr) {
+                float4 h, l;
+                tf32_hi_lo(o.x, h.x, l.x); tf32_hi_lo(o.y, h.y, l.y); tf32_hi_lo(o.z, h.z, l.z); tf32_hi_lo(o.w, h.w, l.w);
+                const size_t off = (size_t)row * p.ldc + col;
+                *reinterpret_cast<float4*>(p.Chi + off) = h;
+                *reinterpret_cast<float4*>(p.Clo + off) = l;
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -286,7 +327,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                   float o = v[j4 + j];
                   if (p.accumulate) o += cp[j4 + j];
                   if (p.bias != nullptr) o += __ldg(p.bias + col + j);
-                  cp[j4 + j] = act_fwd(o, p.act);
+                  o = act_fwd(o, p.act);
+                  cp[j4 + j] = o;
+                  if (p.Chi != nullptr) {
+                    float h, l;
+                    tf32_hi_lo(o, h, l);
+                    p.Chi[(size_t)row * p.ldc + col + j] = h;
+                    p.Clo[(size_t)row * p.ldc + col + j] = l;
+                  }
                 }
             }
           }
@@ -298,7 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
   }
 }
 
@@ -309,14 +358,7 @@ __global__ void tf32_split_rna_kernel(const float* __restrict__ x, float* __rest
     float4 v = reinterpret_cast<const float4*>(x)[i];
     float in[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t hb, lb;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[j]));
-      h[j] = __uint_as_float(hb);
-      float rem = in[j] - h[j];
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
-      l[j] = __uint_as_float(lb);
-    }
+    for (int j = 0; j < 4; ++j) tf32_hi_lo(in[j], h[j], l[j]);
     reinterpret_cast<float4*>(hi)[i] = make_float4(h[0], h[1], h[2], h[3]);
     reinterpret_cast<float4*>(lo)[i] = make_float4(l[0], l[1], l[2], l[3]);
   }
@@ -415,31 +457,12 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUt
   return launch_tc<BN, true, true, NPROD>(mA, mAlo, mB, mBlo, p, st);
 }
 
-int gemm_tc(int mode, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-            float* C, int ldc, const float* bias, int act, int accumulate, void* ws, uint64_t ws_bytes,
-            cudaStream_t st) {
-  const bool x3 = mode == IPAVSR_GEMM_TF32X3;
+// core: operands already split (3xTF32) or raw (TF32: *lo ignored)
+static int gemm_tc_core(bool x3, int transA, int transB, int M, int N, int K, const float* Ahi, const float* Alo, int lda,
+                        const float* Bhi, const float* Blo, int ldb, float* C, int ldc, const float* bias, int act,
+                        int accumulate, float* Chi, float* Clo, cudaStream_t st) {
   const bool a_mn = transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;     // B stored [K,N]: N contiguous
-  const float *Ahi = A, *Alo = A, *Bhi = B, *Blo = B;
-  if (x3) {
-    const size_t a_n = operand_floats(transA ? K : M, lda), b_n = operand_floats(transB ? N : K, ldb);
-    const size_t need = (2 * a_n + 2 * b_n + 16) * sizeof(float);
-    if (ws == nullptr || ws_bytes < need) {
-      set_error("gemm_tc: workspace too small (%llu < %llu bytes)", (unsigned long long)ws_bytes,
-                (unsigned long long)need);
-      return IPAVSR_ERR_ARG;
-    }
-    float* w = reinterpret_cast<float*>(ws);
-    float *ah = w, *al = w + a_n, *bh = w + 2 * a_n, *bl = w + 2 * a_n + b_n;
-    const int cap = sm_count() * 8;
-    size_t a4 = a_n / 4, b4 = b_n / 4;
-    tf32_split_rna_kernel<<<(int)((a4 + 255) / 256 < (size_t)cap ? (a4 + 255) / 256 : cap), 256, 0, st>>>(A, ah, al, a4);
-    IPAVSR_LAUNCH_CHECK();
-    tf32_split_rna_kernel<<<(int)((b4 + 255) / 256 < (size_t)cap ? (b4 + 255) / 256 : cap), 256, 0, st>>>(B, bh, bl, b4);
-    IPAVSR_LAUNCH_CHECK();
-    Ahi = ah; Alo = al; Bhi = bh; Blo = bl;
-  }
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap mA, mAlo, mB, mBlo;
   int rc;
@@ -460,17 +483,24 @@ int gemm_tc(int mode, int transA, int transB, int M, int N, int K, const float* 
   }
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
+  p.Chi = Chi; p.Clo = Clo;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
   int splits = 1;
-  if (act == IPAVSR_ACT_LINEAR && tiles * 2 <= sm_count() && num_kb >= 32) {
-    splits = sm_count() / tiles;
-    if (splits > num_kb / 8) splits = num_kb / 8;
-    if (splits > 32) splits = 32;
+  if (act == IPAVSR_ACT_LINEAR && Chi == nullptr) {
+    if (tiles * 2 <= sm_count() && num_kb >= 32) {         // fill the machine for skinny outputs
+      splits = sm_count() / tiles;
+      if (splits > num_kb / 8) splits = num_kb / 8;
+    }
+    // bound the accumulations into one TMEM accumulator (truncating adds): at most 64 k-blocks (K = 2048) per split
+    const int acc_splits = (num_kb + 63) / 64;
+    if (x3 && acc_splits > splits) splits = acc_splits;
+    if (splits > 64) splits = 64;
     if (splits < 1) splits = 1;
   }
   p.kb_per_split = (num_kb + splits - 1) / splits;
   splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  if (splits < 1) splits = 1;
   p.splits = splits;
   if (splits > 1 && !accumulate)
     IPAVSR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
@@ -481,6 +511,46 @@ int gemm_tc(int mode, int transA, int transB, int M, int N, int K, const float* 
   if (BN == 128) { IPAVSR_TC_DISPATCH(128); }
   IPAVSR_TC_DISPATCH(256);
 #undef IPAVSR_TC_DISPATCH
+}
+
+int tf32_split_launch(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  const int cap = sm_count() * 8;
+  size_t n4 = n / 4;
+  if (n4 == 0) return IPAVSR_OK;
+  tf32_split_rna_kernel<<<(int)((n4 + 255) / 256 < (size_t)cap ? (n4 + 255) / 256 : cap), 256, 0, st>>>(x, hi, lo, n4);
+  IPAVSR_LAUNCH_CHECK();
+  return IPAVSR_OK;
+}
+
+int gemm_tc(int mode, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+            float* C, int ldc, const float* bias, int act, int accumulate, void* ws, uint64_t ws_bytes,
+            cudaStream_t st) {
+  const bool x3 = mode == IPAVSR_GEMM_TF32X3;
+  const float *Ahi = A, *Alo = A, *Bhi = B, *Blo = B;
+  if (x3) {
+    const size_t a_n = operand_floats(transA ? K : M, lda), b_n = operand_floats(transB ? N : K, ldb);
+    const size_t need = (2 * a_n + 2 * b_n + 16) * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) {
+      set_error("gemm_tc: workspace too small (%llu < %llu bytes)", (unsigned long long)ws_bytes,
+                (unsigned long long)need);
+      return IPAVSR_ERR_ARG;
+    }
+    float* w = reinterpret_cast<float*>(ws);
+    float *ah = w, *al = w + a_n, *bh = w + 2 * a_n, *bl = w + 2 * a_n + b_n;
+    int rc;
+    if ((rc = tf32_split_launch(A, ah, al, a_n, st))) return rc;
+    if ((rc = tf32_split_launch(B, bh, bl, b_n, st))) return rc;
+    Ahi = ah; Alo = al; Bhi = bh; Blo = bl;
+  }
+  return gemm_tc_core(x3, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate, nullptr,
+                      nullptr, st);
+}
+
+int gemm_tc_presplit(int transA, int transB, int M, int N, int K, const float* Ahi, const float* Alo, int lda,
+                     const float* Bhi, const float* Blo, int ldb, float* C, int ldc, const float* bias, int act,
+                     int accumulate, float* Chi, float* Clo, cudaStream_t st) {
+  return gemm_tc_core(true, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate, Chi,
+                      Clo, st);
 }
 
 }  // namespace ipavsr

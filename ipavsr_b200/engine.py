@@ -122,6 +122,8 @@ class ParamArena(object):
         self.grad = torch.zeros(total, dtype=torch.float32, device=device)
         self.aux = torch.zeros(max(aux, 4), dtype=torch.float32, device=device)
         self.state = {}
+        self.flat_hi = self.flat_lo = None      # tf32 split of the parameters (3xTF32 mode), refreshed when dirty
+        self.split_dirty = True
         # upload host masters, then bind
         params = list(self.bind.keys())
         for p in params:
@@ -165,6 +167,7 @@ class ParamArena(object):
         return self._view(buf, p).detach().cpu().numpy().astype(np.float32).reshape(p.shape).copy()
 
     def write(self, p, value):
+        self.split_dirty = True
         v = self._view(self.flat, p)
         v.copy_(torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32)).reshape(v.shape))
 
@@ -175,6 +178,30 @@ class ParamArena(object):
 
     def tensor_of(self, p):
         return self.bind[p][0]
+
+
+class _Profiler(object):
+    """Optional per-entry-point device timing (IPAVSR_PROFILE=1): CUDA events around every C-ABI call, summed by
+    entry-point name.  Off by default (it adds event overhead); used by tools/profile_step.py."""
+
+    def __init__(self):
+        self.events = []
+
+    def call(self, name, *args):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(getattr(_lib.load(), name)(*args), name)
+        e1.record()
+        self.events.append((name, e0, e1))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.events:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + e0.elapsed_time(e1))
+        self.events = []
+        return out
 
 
 class _Run(object):
@@ -214,7 +241,7 @@ class Engine(object):
         self.world = None            # (rank, world_size, group) when data-parallel
         self.step_t = np.float32(0)  # Adam's shared step counter (custom/updates.py:74)
         self._ws = None
-        self._gemm_ws = None
+        self._split_cache = {}
         self._lr_cache = None
 
     # ------------------------------------------------------------------------------------------------
@@ -235,24 +262,65 @@ class Engine(object):
             self._ws = torch.empty((int(nbytes) + 3) // 4, dtype=torch.float32, device=self.device)
         return self._ws
 
-    def gemm(self, A, B, Cm, M, N, K, transA=0, transB=0, bias=None, act=0, accumulate=0):
-        ws_ptr, ws_bytes = None, 0
-        if self.gemm_mode != 0:
-            need = self.lib.ipavsr_gemm_workspace_bytes(self.gemm_mode, transA, transB, M, N, K)
-            if need:
-                if self._gemm_ws is None or self._gemm_ws.numel() * 4 < need:
-                    self._gemm_ws = torch.empty((int(need) + 3) // 4, dtype=torch.float32, device=self.device)
-                ws_ptr, ws_bytes = self._gemm_ws.data_ptr(), int(need)
-        _lib.call('ipavsr_gemm', self.gemm_mode, transA, transB, M, N, K, A.ptr, A.ld, B.ptr, B.ld, Cm.ptr, Cm.ld,
-                  bias, act, accumulate, ws_ptr, ws_bytes, self.stream)
+    # ---- 3xTF32 operand splits: each tensor is split once per step and reused by every GEMM that reads it ----
+    def _refresh_param_split(self):
+        ar = self.arena
+        if ar.flat_hi is None:
+            ar.flat_hi = torch.empty_like(ar.flat)
+            ar.flat_lo = torch.empty_like(ar.flat)
+        if ar.split_dirty:
+            _lib.call('ipavsr_tf32_split_rna', ar.flat.data_ptr(), ar.flat_hi.data_ptr(), ar.flat_lo.data_ptr(),
+                      ar.flat.numel(), self.stream)
+            ar.split_dirty = False
 
-    def _proj(self, segs, W, out, bias, act):
+    def _split_of(self, m):
+        """(hi, lo) DevMats of an operand: parameters come from the split arenas, activations are split on first use."""
+        ar = self.arena
+        if m.t is ar.flat:
+            off = m.ptr - ar.flat.data_ptr()
+            return (DevMat(ar.flat_hi, ar.flat_hi.data_ptr() + off, m.rows, m.cols, m.ld),
+                    DevMat(ar.flat_lo, ar.flat_lo.data_ptr() + off, m.rows, m.cols, m.ld))
+        key = (m.ptr, m.rows, m.cols, m.ld)
+        hit = self._split_cache.get(key)
+        if hit is None:
+            n = (m.rows * m.ld + 3) // 4 * 4
+            hi = torch.empty(n, dtype=torch.float32, device=self.device)
+            lo = torch.empty(n, dtype=torch.float32, device=self.device)
+            _lib.call('ipavsr_tf32_split_rna', m.ptr, hi.data_ptr(), lo.data_ptr(), n, self.stream)
+            hit = (DevMat(hi, hi.data_ptr(), m.rows, m.cols, m.ld), DevMat(lo, lo.data_ptr(), m.rows, m.cols, m.ld), m.t)
+            self._split_cache[key] = hit
+        return hit[0], hit[1]
+
+    def gemm(self, A, B, Cm, M, N, K, transA=0, transB=0, bias=None, act=0, accumulate=0, emit_split=False):
+        mode = self.gemm_mode
+        if mode != 0 and not self.lib.ipavsr_gemm_tc_supported(transA, transB, M, N, K, A.ptr, A.ld, B.ptr, B.ld,
+                                                                Cm.ptr, Cm.ld):
+            mode = 0        # tiny / unaligned products: the exact FP32 kernel
+        if mode == 1:
+            ah, al = self._split_of(A)
+            bh, bl = self._split_of(B)
+            chi = clo = None
+            if emit_split and not accumulate:
+                n = (Cm.rows * Cm.ld + 3) // 4 * 4
+                th = torch.empty(n, dtype=torch.float32, device=self.device)
+                tl = torch.empty(n, dtype=torch.float32, device=self.device)
+                chi, clo = th.data_ptr(), tl.data_ptr()
+                self._split_cache[(Cm.ptr, Cm.rows, Cm.cols, Cm.ld)] = (
+                    DevMat(th, chi, Cm.rows, Cm.cols, Cm.ld), DevMat(tl, clo, Cm.rows, Cm.cols, Cm.ld), Cm.t)
+            _lib.call('ipavsr_gemm_tf32x3_presplit', transA, transB, M, N, K, ah.ptr, al.ptr, A.ld, bh.ptr, bl.ptr, B.ld,
+                      Cm.ptr, Cm.ld, bias, act, accumulate, chi, clo, self.stream)
+            return
+        _lib.call('ipavsr_gemm', mode, transA, transB, M, N, K, A.ptr, A.ld, B.ptr, B.ld, Cm.ptr, Cm.ld,
+                  bias, act, accumulate, None, 0, self.stream)
+
+    def _proj(self, segs, W, out, bias, act, emit_split=False):
         """out = act( [segs...] @ W + bias ): the concat is walked as a K-split accumulate."""
         k0 = 0
         for i, a in enumerate(segs):
             last = i == len(segs) - 1
             self.gemm(a, W.row_slice(k0, a.cols), out, a.rows, out.cols, a.cols, 0, 0,
-                      bias if last else None, act if last else 0, 1 if i > 0 else 0)
+                      bias if last else None, act if last else 0, 1 if i > 0 else 0,
+                      emit_split=emit_split and len(segs) == 1)
             k0 += a.cols
 
     # ------------------------------------------------------------------------------------------------
@@ -297,6 +365,9 @@ class Engine(object):
                 break
         N, T = int(first.shape[0]), int(first.shape[1])
         run = _Run(N, T)
+        self._split_cache = {}
+        if self.gemm_mode == 1:
+            self._refresh_param_split()
         run.window = int(window) if window is not None else 0
         run.deterministic = deterministic
         ar = self.arena
@@ -319,7 +390,7 @@ class Engine(object):
                     self._proj(segs, W, logits, b, 0)
                     _lib.call('ipavsr_softmax', logits.ptr, logits.ld, out.ptr, out.ld, rows, l.num_units, st)
                 else:
-                    self._proj(segs, W, out, b, ACT[l.nonlinearity.name])
+                    self._proj(segs, W, out, b, ACT[l.nonlinearity.name], emit_split=True)
                 run.vals[l] = [out]
             elif isinstance(l, L.BatchNormLayer):
                 x = run.vals[l.input_layer][0]
@@ -674,6 +745,8 @@ class Engine(object):
 
     def optim_step(self, kind, lr, params=None, lr_map=None, **hp):
         ar, st = self.arena, self.stream
+        ar.split_dirty = True
+        self._split_cache = {}
         n = ar.n
         seg_lr = seg_id = None
         if lr_map is not None:

@@ -11,9 +11,9 @@ mode, ta, tb, M, N, K = [int(x) for x in sys.argv[1:7]]
 print('mode %%d ta %%d tb %%d M %%d N %%d K %%d err %%.3e' %% (mode, ta, tb, M, N, K, _run(mode, ta, tb, M, N, K)), flush=True)
 ''' % (os.path.dirname(HERE), os.path.dirname(HERE))
 cases = []
-for mode in (2, 1):
-    for ta, tb in ((0, 0), (1, 1), (1, 0)):
-        for (M, N, K) in ((128, 64, 512), (1040, 2000, 1200)):
+for mode in (1,):
+    for ta, tb in ((0, 0), (1, 0)):
+        for (M, N, K) in ((2048, 52, 500), (1040, 128, 1200), (1040, 2000, 1200), (1200, 2000, 4096), (1200, 2000, 20480)):
             cases.append((mode, ta, tb, M, N, K))
 for c in cases:
     try:

