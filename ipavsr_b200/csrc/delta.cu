@@ -6,7 +6,7 @@
 // (float32 subtraction, float64 product/quotient/add, float32 round after every theta), then the same operator
 // on d gives a; output row = [x | d | a].  The layer is mask-agnostic and runs over the whole padded T.
 //
-// Kernel: a CTA stages UPC utterances' (T x F) tiles in shared memory (coalesced row loads), every thread owns a
+// General kernel (any T, any Theta): a CTA stages UPC utterances' (T x F) tiles in shared memory (coalesced row loads), every thread owns a
 // (utterance, feature, 4-frame run) and slides a register window of 2*Theta+4 frames over it (window loads are
 // bank-conflict-free: lanes walk the feature axis), writes d back to shared memory, repeats for a, then the CTA
 // streams the [x|d|a] rows out coalesced.  Algorithmic traffic 16*F bytes/frame (read 4F, write 12F): HBM-bound.
@@ -176,6 +176,77 @@ __global__ void __launch_bounds__(DELTA_THREADS) delta_bwd_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Column kernel (the fast path: T <= 48 and Theta in {1,4,9}).  One THREAD owns one (utterance, feature) column and
+// keeps the whole column in registers: TMAX + 2*Theta edge-replicated frames of x (the clamp is folded into the load
+// address, so every register index is static), then d, then a.  No shared memory, no barriers; a warp's loads and
+// stores at a fixed t cover 32 consecutive features = one 128-byte line; every thread has ~60 independent loads in
+// flight, which is what keeps HBM busy.  Frames t >= T of the TMAX template are computed on clamped data and
+// discarded.
+// ---------------------------------------------------------------------------------------------------------
+template <int TH, int TMAX, bool EXACT>
+__global__ void __launch_bounds__(128) delta_fwd_col_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
+                                                            int ldy, int N, int T, int F) {
+  const long long total = (long long)N * F;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+       c += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(c / F), f = (int)(c % F);
+    const float* xc = x + (size_t)n * T * ldx + f;
+    float* yc = y + (size_t)n * T * ldy + f;
+    float xs[TMAX + 2 * TH];
+#pragma unroll
+    for (int i = 0; i < TMAX + 2 * TH; ++i) {
+      const int t = min(max(i - TH, 0), T - 1);
+      xs[i] = __ldg(xc + (size_t)t * ldx);
+    }
+    float d[TMAX];
+    float dlast = 0.f;
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      float acc = 0.f;
+#pragma unroll
+      for (int th = 1; th <= TH; ++th) acc = delta_step<EXACT>(acc, xs[t + TH + th] - xs[t + TH - th], th);
+      d[t] = acc;
+      if (t == T - 1) dlast = acc;
+      if (t < T) {
+        __stcs(yc + (size_t)t * ldy, xs[t + TH]);
+        __stcs(yc + (size_t)t * ldy + F, acc);
+      }
+    }
+    // a[t] from the edge-replicated d: index clamp(t +- th, 0, T-1); static register indices, runtime select for >= T
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) {
+      float acc = 0.f;
+#pragma unroll
+      for (int th = 1; th <= TH; ++th) {
+        const int ip = t + th, im = t - th;
+        const float hi = ip < TMAX ? (ip < T ? d[ip < TMAX ? ip : 0] : dlast) : dlast;
+        const float lo = d[im > 0 ? im : 0];
+        acc = delta_step<EXACT>(acc, hi - lo, th);
+      }
+      if (t < T) __stcs(yc + (size_t)t * ldy + 2 * F, acc);
+    }
+  }
+}
+
+template <int TH, int TMAX, bool EXACT>
+static int launch_delta_col(const float* x, int ldx, float* y, int ldy, int N, int T, int F, cudaStream_t st) {
+  const long long total = (long long)N * F;
+  long long blocks = (total + 127) / 128;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  delta_fwd_col_kernel<TH, TMAX, EXACT><<<(int)blocks, 128, 0, st>>>(x, ldx, y, ldy, N, T, F);
+  IPAVSR_LAUNCH_CHECK();
+  return IPAVSR_OK;
+}
+
+template <int TH, bool EXACT>
+static int dispatch_delta_col(const float* x, int ldx, float* y, int ldy, int N, int T, int F, cudaStream_t st) {
+  if (T <= 24) return launch_delta_col<TH, 24, EXACT>(x, ldx, y, ldy, N, T, F, st);
+  if (T <= 40) return launch_delta_col<TH, 40, EXACT>(x, ldx, y, ldy, N, T, F, st);
+  return launch_delta_col<TH, 48, EXACT>(x, ldx, y, ldy, N, T, F, st);
+}
+
 template <int TH, bool EXACT>
 static int launch_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, int T, int F, int theta, int upc,
                             int grid, size_t smem, cudaStream_t st) {
@@ -198,6 +269,15 @@ int ipavsr_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, int T, i
   IPAVSR_CHECK_ARG(ldx >= F && ldy >= 3 * F, "leading dimensions too small");
   if (N == 0) return IPAVSR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (T <= 48 && (theta == 1 || theta == 4 || theta == 9)) {
+    // register-resident column kernel (every shipped configuration: T <= 40, theta = 9)
+    if (theta == 1) return exact ? dispatch_delta_col<1, true>(x, ldx, y, ldy, N, T, F, st)
+                                 : dispatch_delta_col<1, false>(x, ldx, y, ldy, N, T, F, st);
+    if (theta == 4) return exact ? dispatch_delta_col<4, true>(x, ldx, y, ldy, N, T, F, st)
+                                 : dispatch_delta_col<4, false>(x, ldx, y, ldy, N, T, F, st);
+    return exact ? dispatch_delta_col<9, true>(x, ldx, y, ldy, N, T, F, st)
+                 : dispatch_delta_col<9, false>(x, ldx, y, ldy, N, T, F, st);
+  }
   const size_t per_utt = (size_t)3 * T * F * sizeof(float);
   IPAVSR_CHECK_ARG(per_utt <= 200 * 1024, "one utterance tile (3*T*F floats) must fit in 200 KB of shared memory");
   // utterances per CTA: aim for ~36 KB of shared memory per CTA so ~6 CTAs stay resident per SM

@@ -235,6 +235,23 @@ lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hi
   }
   cluster.sync();   // everyone's hT[0] / Ws initialised before any remote write can land
 
+  // software pipeline over time: the gate pre-activations (and mask) of step s+1 are fetched while step s computes
+  float4 xn[4];
+  bool mnext[4];
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      xn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mnext[i] = false;
+      if (n_ok[i] && u_ok) {
+        size_t row = (size_t)ng[i] * T + t;
+        xn[i] = __ldg(reinterpret_cast<const float4*>(xw + row * H4 + 4 * ug));
+        mnext[i] = mask[row] != 0;
+      }
+    }
+  };
+  fetch(backwards ? (T - 1) : 0);
+
   int cur = 0;
   for (int s = 0; s < T; ++s) {
     const int t = backwards ? (T - 1 - s) : s;
@@ -242,15 +259,10 @@ lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hi
     bool m[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      m[i] = false;
-      if (n_ok[i] && u_ok) {
-        size_t row = (size_t)ng[i] * T + t;
-        x4 = __ldg(reinterpret_cast<const float4*>(xw + row * H4 + 4 * ug));
-        m[i] = mask[row] != 0;
-      }
-      acc[i][0] = x4.x; acc[i][1] = x4.y; acc[i][2] = x4.z; acc[i][3] = x4.w;
+      acc[i][0] = xn[i].x; acc[i][1] = xn[i].y; acc[i][2] = xn[i].z; acc[i][3] = xn[i].w;
+      m[i] = mnext[i];
     }
+    if (s + 1 < T) fetch(backwards ? (T - 2 - s) : (s + 1));
     const float* hcur = hT + (size_t)cur * Hpad * LNT;
 #pragma unroll 4
     for (int k = 0; k < H; ++k) {
@@ -267,33 +279,37 @@ lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hi
         acc[i][3] = fmaf(hh[i], wv.w, acc[i][3]);
       }
     }
-    float hnew[4];
     float4 hp4 = *reinterpret_cast<const float4*>(hcur + (size_t)(u_ok ? ug : 0) * LNT + n0);
     const float hpv[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+    CellOut r[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      CellOut r = lstm_cell_fwd(acc[i][0], acc[i][1], acc[i][2], acc[i][3], c_prev[i], hpv[i], m[i], has_peep, w_ci,
-                                w_cf, w_co);
-      hnew[i] = r.h;
-      c_prev[i] = r.c;
-      if (n_ok[i] && u_ok) {
-        size_t row = (size_t)ng[i] * T + t;
-        out[row * ldh + ug] = r.h;
-        if (gates) *reinterpret_cast<float4*>(gates + row * H4 + 4 * ug) = make_float4(r.i, r.f, r.cin, r.o);
-        if (cell) cell[row * H + ug] = r.c;
-        if (hprev) hprev[row * ldh + ug] = hpv[i];
-      }
+      r[i] = lstm_cell_fwd(acc[i][0], acc[i][1], acc[i][2], acc[i][3], c_prev[i], hpv[i], m[i], has_peep, w_ci, w_cf,
+                           w_co);
+      c_prev[i] = r[i].c;
     }
-    // broadcast the new h of my (4 utterances, 1 unit) to every CTA of the cluster
+    // broadcast the new h of my (4 utterances, 1 unit) to every CTA of the cluster, then arrive on the cluster
+    // barrier BEFORE the global stores of this step: the barrier's release then only has to cover the DSMEM writes,
+    // and the global stores drain underneath the next step's matmul.
     if (u_ok) {
       float* mine = hT + (size_t)(cur ^ 1) * Hpad * LNT + (size_t)ug * LNT + n0;
-      const float4 hv = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+      const float4 hv = make_float4(r[0].h, r[1].h, r[2].h, r[3].h);
       for (int rr = 0; rr < CS; ++rr) {
         float4* dst = reinterpret_cast<float4*>(cluster.map_shared_rank(mine, rr));
         *dst = hv;
       }
     }
-    cluster.sync();
+    cluster.barrier_arrive();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n_ok[i] && u_ok) {
+        size_t row = (size_t)ng[i] * T + t;
+        out[row * ldh + ug] = r[i].h;
+        if (gates) *reinterpret_cast<float4*>(gates + row * H4 + 4 * ug) = make_float4(r[i].i, r[i].f, r[i].cin, r[i].o);
+        if (cell) cell[row * H + ug] = r[i].c;
+        if (hprev) hprev[row * ldh + ug] = hpv[i];
+      }
+    cluster.barrier_wait();
     cur ^= 1;
   }
 }
@@ -355,10 +371,33 @@ lstm_bwd_persistent(const float* __restrict__ dout, const float* __restrict__ wT
   float dh_pass[4] = {0.f, 0.f, 0.f, 0.f};
   cluster.sync();
 
+  // software pipeline over time: the saved tensors of the next processed step are fetched during the matmul
+  float pf_dout[4], pf_c[4], pf_cp[4];
+  float4 pf_g[4];
+  bool pf_m[4];
+  auto fetch = [&](int s) {
+    const int t = backwards ? (T - 1 - s) : s;
+    const int t_prev = (s == 0) ? -1 : (backwards ? t + 1 : t - 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pf_dout[i] = pf_c[i] = pf_cp[i] = 0.f;
+      pf_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pf_m[i] = false;
+      if (n_ok[i] && u_ok) {
+        size_t row = (size_t)ng[i] * T + t;
+        pf_dout[i] = __ldg(dout + row * ldh + ug);
+        pf_g[i] = __ldg(reinterpret_cast<const float4*>(gates + row * H4 + 4 * ug));
+        pf_c[i] = __ldg(cell + row * H + ug);
+        pf_cp[i] = t_prev < 0 ? cell_init[ug] : __ldg(cell + ((size_t)ng[i] * T + t_prev) * H + ug);
+        pf_m[i] = mask[row] != 0;
+      }
+    }
+  };
+  fetch(T - 1);
+
   int par = 0;
   for (int s = T - 1; s >= 0; --s) {                   // reverse of the processing order
     const int t = backwards ? (T - 1 - s) : s;
-    const int t_prev = (s == 0) ? -1 : (backwards ? t + 1 : t - 1);
     // ---- 1. elementwise gate gradients for my (4 utterances, 1 unit) ----
     float4 dgv[4];
 #pragma unroll
@@ -367,12 +406,9 @@ lstm_bwd_persistent(const float* __restrict__ dout, const float* __restrict__ wT
       dh_pass[i] = 0.f;
       if (n_ok[i] && u_ok) {
         size_t row = (size_t)ng[i] * T + t;
-        float dh = __ldg(dout + row * ldh + ug) + dh_next[i];
-        float4 g4 = __ldg(reinterpret_cast<const float4*>(gates + row * H4 + 4 * ug));
-        float c = __ldg(cell + row * H + ug);
-        float cp = t_prev < 0 ? cell_init[ug] : __ldg(cell + ((size_t)ng[i] * T + t_prev) * H + ug);
-        bool m = mask[row] != 0;
-        CellGrad g = lstm_cell_bwd(dh, dc_next[i], g4.x, g4.y, g4.z, g4.w, c, cp, m, has_peep, w_ci, w_cf, w_co, clip);
+        float dh = pf_dout[i] + dh_next[i];
+        CellGrad g = lstm_cell_bwd(dh, dc_next[i], pf_g[i].x, pf_g[i].y, pf_g[i].z, pf_g[i].w, pf_c[i], pf_cp[i],
+                                   pf_m[i], has_peep, w_ci, w_cf, w_co, clip);
         dgv[i] = make_float4(g.dgi, g.dgf, g.dgc, g.dgo);
         dc_next[i] = g.dc_prev;
         dh_pass[i] = g.dh_pass;
@@ -380,6 +416,7 @@ lstm_bwd_persistent(const float* __restrict__ dout, const float* __restrict__ wT
         *reinterpret_cast<float4*>(dgates + row * H4 + 4 * ug) = dgv[i];
       }
     }
+    if (s > 0) fetch(s - 1);
     // dgT[jj][n], jj = 4*ul + gate
     *reinterpret_cast<float4*>(dgT + (size_t)(4 * ul + 0) * LNT + n0) = make_float4(dgv[0].x, dgv[1].x, dgv[2].x, dgv[3].x);
     *reinterpret_cast<float4*>(dgT + (size_t)(4 * ul + 1) * LNT + n0) = make_float4(dgv[0].y, dgv[1].y, dgv[2].y, dgv[3].y);

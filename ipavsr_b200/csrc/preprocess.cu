@@ -133,15 +133,18 @@ __global__ void featurewise_finalize_kernel(const double* __restrict__ scratch, 
   std[c] = (float)sqrt(var > 0 ? var : 0.0);
 }
 
-__global__ void featurewise_apply_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mean,
-                                         const float* __restrict__ std, float* __restrict__ y, int ldy, int64_t frames,
-                                         int F) {
-  const int64_t total = frames * F;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = i / F;
-    int c = (int)(i % F);
-    __stcs(y + r * ldy + c, (__ldcs(x + r * ldx + c) - mean[c]) / std[c]);
-  }
+// grid (column chunks of 128 floats as float4 lanes, row groups); threads walk rows, lanes walk features
+__global__ void __launch_bounds__(256) featurewise_apply_kernel(const float* __restrict__ x, int ldx,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ std, float* __restrict__ y,
+                                                                int ldy, int64_t frames, int F, int rows_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  if (c >= F) return;
+  const float m = mean[c], sd = std[c];
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < frames ? r0 + rows_per_block : frames;
+  for (int64_t r = r0 + rl; r < r1; r += 8) __stcs(y + r * ldy + c, (__ldcs(x + r * ldx + c) - m) / sd);
 }
 
 // ---- a12 sequencewise_mean_image_subtraction (:260-277) and a14 compute_diff_images (:506-517) ----
@@ -172,10 +175,23 @@ __global__ void __launch_bounds__(128) diff_image_kernel(const float* __restrict
     return;
   }
   float prev = __ldcs(x + b * ldx + c);
-  for (int64_t r = b + 1; r < e; ++r) {
+  int64_t r = b + 1;
+  // four independent row loads in flight per thread
+  for (; r + 3 < e; r += 4) {
+    float c0 = __ldcs(x + r * ldx + c), c1 = __ldcs(x + (r + 1) * ldx + c), c2 = __ldcs(x + (r + 2) * ldx + c),
+          c3 = __ldcs(x + (r + 3) * ldx + c);
+    float d0 = c0 - prev;
+    if (r == b + 1) __stcs(y + b * ldy + c, d0);   // frame 0 duplicates the first difference (:514-515)
+    __stcs(y + r * ldy + c, d0);
+    __stcs(y + (r + 1) * ldy + c, c1 - c0);
+    __stcs(y + (r + 2) * ldy + c, c2 - c1);
+    __stcs(y + (r + 3) * ldy + c, c3 - c2);
+    prev = c3;
+  }
+  for (; r < e; ++r) {
     float cur = __ldcs(x + r * ldx + c);
     float d = cur - prev;
-    if (r == b + 1) __stcs(y + b * ldy + c, d);   // frame 0 duplicates the first difference (:514-515)
+    if (r == b + 1) __stcs(y + b * ldy + c, d);
     __stcs(y + r * ldy + c, d);
     prev = cur;
   }
@@ -267,8 +283,10 @@ int ipavsr_norm_featurewise_apply(const float* x, int ldx, const float* mean, co
                                   int64_t frames, int F, void* stream) {
   IPAVSR_CHECK_ARG(x && mean && std && y && frames >= 0 && F >= 1, "bad arguments");
   if (frames == 0) return IPAVSR_OK;
-  featurewise_apply_kernel<<<grid_cap((frames * F + 255) / 256, 8), 256, 0, S(stream)>>>(x, ldx, mean, std, y, ldy,
-                                                                                         frames, F);
+  int rows_per_block = 64;
+  while ((frames + rows_per_block - 1) / rows_per_block > 60000) rows_per_block *= 2;
+  dim3 grid((F + 31) / 32, (unsigned)((frames + rows_per_block - 1) / rows_per_block));
+  featurewise_apply_kernel<<<grid, 256, 0, S(stream)>>>(x, ldx, mean, std, y, ldy, frames, F, rows_per_block);
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }

@@ -212,6 +212,9 @@ class _Run(object):
         self.vals = {}
         self.saved = {}
         self.grads = {}
+        self.pending = {}       # layer -> CUDA event of work still running on a side stream
+        self.bwd_ready = {}     # LSTM layer -> (event, dG) launched ahead of the backward walk
+        self.keep = []          # buffers that must outlive the side-stream kernels
 
 
 class Engine(object):
@@ -243,6 +246,11 @@ class Engine(object):
         self._ws = None
         self._split_cache = {}
         self._lr_cache = None
+        # independent LSTM recurrences (the per-stream LSTMs; the forward/backward aggregate pair) run concurrently
+        # on side streams and overlap with the GEMMs of the other branches on the main stream
+        self.concurrent_lstm = os.environ.get('IPAVSR_CONCURRENT_LSTM', '1') != '0'
+        self._side = []
+        self._side_next = 0
 
     # ------------------------------------------------------------------------------------------------
     # small helpers
@@ -256,6 +264,32 @@ class Engine(object):
         n = max(rows * ld, 4)
         t = (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=self.device)
         return DevMat(t, t.data_ptr(), rows, cols, ld)
+
+    def _side_stream(self):
+        if not self._side:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+        st = self._side[self._side_next % len(self._side)]
+        self._side_next += 1
+        return st
+
+    def _fork(self):
+        """Returns (side stream, its handle) ordered after everything queued so far on the main stream."""
+        side = self._side_stream()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        side.wait_event(ev)
+        return side, C.c_void_p(side.cuda_stream)
+
+    def _wait(self, run, layer):
+        ev = run.pending.pop(layer, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _join(self, run):
+        for layer in list(run.pending.keys()):
+            self._wait(run, layer)
+        for layer, (ev, _) in list(run.bwd_ready.items()):
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() * 4 < nbytes:
@@ -372,6 +406,9 @@ class Engine(object):
         run.deterministic = deterministic
         ar = self.arena
         for l in self.layers:
+            for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
+                if i is not None and i in run.pending and not (isinstance(l, L.LSTMLayer) and i in self.mask_layers):
+                    self._wait(run, i)
             if isinstance(l, L.InputLayer):
                 if l in self.mask_layers:
                     run.vals[l] = self._upload(inputs[l], 'mask')
@@ -464,11 +501,23 @@ class Engine(object):
                         cell = DevMat(cell.t, cell.ptr, N * T, H, H)
                 peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
                 nbytes = lib.ipavsr_lstm_workspace_bytes(N, T, H)
-                ws = self._workspace(nbytes)
+                if self.concurrent_lstm:
+                    ws = torch.empty((int(nbytes) + 3) // 4, dtype=torch.float32, device=self.device) \
+                        if self.lstm_impl != 0 else self._workspace(16)
+                    run.keep.append(ws)
+                    side, sh = self._fork()
+                else:
+                    ws, side, sh = self._workspace(nbytes), None, st
                 _lib.call('ipavsr_lstm_fwd', xw.ptr, ar.mat((l, 'W_hid')).ptr, peep, ar.mat((l, 'cell_init')).ptr,
                           ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
                           gates.ptr if gates else None, cell.ptr if cell else None, hprev.ptr if hprev else None,
-                          N, T, H, out.ld, 1 if l.backwards else 0, self.lstm_impl, ws.data_ptr(), int(nbytes), st)
+                          N, T, H, out.ld, 1 if l.backwards else 0, self.lstm_impl, ws.data_ptr(),
+                          int(nbytes) if (self.lstm_impl != 0 or not self.concurrent_lstm) else 16, sh)
+                if side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    run.pending[l] = ev
+                run.keep.append(xw)
                 run.saved[l] = (mask, gates, cell, hprev)
                 run.vals[l] = [out]
             elif isinstance(l, (L.ElemwiseSumLayer, L.AdaptiveElemwiseSumLayer)):
@@ -492,6 +541,7 @@ class Engine(object):
                 run.vals[l] = [out]
             else:
                 raise TypeError('unsupported layer type %s' % type(l).__name__)
+        self._join(run)
         return run, run.vals[self.out]
 
     def _single(self, segs):
@@ -549,8 +599,18 @@ class Engine(object):
         if not (isinstance(head, L.DenseLayer) and head.nonlinearity.name == 'softmax'):
             raise ValueError('the network output must be a softmax DenseLayer to train')
         run.grads[head] = ([dlogits], True)
+        # number of not-yet-processed consumers of every layer: when it reaches zero the layer's gradient is final and
+        # an LSTM recurrence can be launched ahead of the walk on a side stream
+        remaining = {}
+        for l in self.layers:
+            for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
+                if i is not None:
+                    remaining[i] = remaining.get(i, 0) + 1
         for l in reversed(self.layers):
+            in_layers = [i for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)])
+                         if i is not None]
             if l not in run.grads or isinstance(l, L.InputLayer):
+                self._release(run, in_layers, remaining)
                 continue
             gsegs, _ = run.grads[l]
             if isinstance(l, L.ReshapeLayer):
@@ -604,19 +664,13 @@ class Engine(object):
                     tgt, acc = self._grad_target(run, l.input_layer, [DevMat(None, 0, g.rows, F, _ld4(F))])
                     _lib.call('ipavsr_delta_bwd', g.ptr, g.ld, tgt[0].ptr, tgt[0].ld, N, T, F, run.window, acc, st)
             elif isinstance(l, L.LSTMLayer):
-                dout = gsegs[0]
                 H = l.num_units
                 mask, gates, cell, hprev = run.saved[l]
-                dG = self.new(N * T, 4 * H)
-                peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
-                dpeep = G((l, 'peep')).ptr if l.peepholes else None
-                nbytes = lib.ipavsr_lstm_workspace_bytes(N, T, H)
-                ws = self._workspace(nbytes)
-                clip = l.grad_clipping if l.grad_clipping else 0.0
-                _lib.call('ipavsr_lstm_bwd', dout.ptr, ar.mat((l, 'W_hid')).ptr, peep, ar.mat((l, 'cell_init')).ptr,
-                          mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,
-                          G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
-                          self.lstm_impl, ws.data_ptr(), int(nbytes), st)
+                if l in run.bwd_ready:
+                    ev, dG = run.bwd_ready.pop(l)
+                    torch.cuda.current_stream(self.device).wait_event(ev)
+                else:
+                    dG = self._lstm_bwd_launch(run, l, gsegs[0], st, None)
                 if not l.learn_init:
                     G((l, 'cell_init')).torch_view().zero_()
                     G((l, 'hid_init')).torch_view().zero_()
@@ -661,6 +715,41 @@ class Engine(object):
             else:
                 raise TypeError('unsupported layer type %s' % type(l).__name__)
             del run.grads[l]
+            self._release(run, in_layers, remaining)
+        self._join(run)
+
+    def _release(self, run, ins, remaining):
+        for i in ins:
+            remaining[i] -= 1
+            if (remaining[i] == 0 and self.concurrent_lstm and isinstance(i, L.LSTMLayer) and i in run.grads
+                    and i not in run.bwd_ready):
+                side, sh = self._fork()
+                dG = self._lstm_bwd_launch(run, i, run.grads[i][0][0], sh, side)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                run.bwd_ready[i] = (ev, dG)
+
+    def _lstm_bwd_launch(self, run, l, dout, stream_handle, side):
+        ar, lib = self.arena, self.lib
+        N, T, H = run.N, run.T, l.num_units
+        G = lambda key: ar.mat(key, 'grad')
+        mask, gates, cell, hprev = run.saved[l]
+        dG = self.new(N * T, 4 * H)
+        peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
+        dpeep = G((l, 'peep')).ptr if l.peepholes else None
+        nbytes = lib.ipavsr_lstm_workspace_bytes(N, T, H)
+        if side is not None:
+            ws = torch.empty((int(nbytes) + 3) // 4, dtype=torch.float32, device=self.device)
+            run.keep.append(ws)
+            run.keep.append(dout.t)
+        else:
+            ws = self._workspace(nbytes)
+        clip = l.grad_clipping if l.grad_clipping else 0.0
+        _lib.call('ipavsr_lstm_bwd', dout.ptr, ar.mat((l, 'W_hid')).ptr, peep, ar.mat((l, 'cell_init')).ptr,
+                  mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,
+                  G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
+                  self.lstm_impl, ws.data_ptr(), int(nbytes), stream_handle)
+        return dG
 
     def _proj_bwd(self, run, in_layer, xsegs, dZ, W, dW):
         """dW[rows of seg] = seg^T dZ ;  d(seg) (+)= dZ W[rows of seg]^T."""

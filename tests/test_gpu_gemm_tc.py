@@ -56,7 +56,7 @@ def test_tf32_single_pass(M, N, K, ta, tb):
 
 @pytest.mark.parametrize('act,acc,use_bias', [(1, 0, True), (2, 1, True), (0, 1, False), (3, 0, True)])
 def test_epilogue_variants(act, acc, use_bias):
-    for mode, tol in ((1, 5e-4), (2, 2e-2)):
+    for mode, tol in ((1, 5e-4), (2, 1e-1)):
         err = _run(mode, 0, 0, 1040, 2000, 1200, act, acc, use_bias)
         assert err < tol, (mode, err)
 
