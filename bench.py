@@ -206,7 +206,8 @@ def main():
     net, v, mask_var, window = build_network()
     eng = get_engine(net, gemm_mode=args.mode)
     if world > 1:
-        eng.world = (rank, world, dist.group.WORLD)
+        from ipavsr_b200 import parallel
+        parallel.attach(eng)
     targets = T.imatrix('targets')
     pred = L.get_output(net, deterministic=False)
     cost = temporal_softmax_loss(pred, targets, mask_var)

@@ -21,6 +21,7 @@
 // impl 1 — one GEMM + one elementwise launch per step (the plain form; kept as an in-library cross-check and
 // as the path for H > 512).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -182,8 +183,14 @@ constexpr int LNT = 32;        // utterances per cluster tile
 constexpr int LU = 32;         // hidden units per CTA
 constexpr int LTHREADS = 256;
 
+// Forward: 512 threads = two K-groups of 256.  Group g accumulates the k = g (mod 2) half of the reduction for the
+// whole 32 x 128 tile (4 utterances x 4 gates per thread), the two halves are exchanged through shared memory so that
+// every thread finalises 2 utterances x 1 unit (balanced cell arithmetic), and 16 warps per SM hide the shared-memory
+// latency of the two LDS.128 per 16 FFMA inner loop.
+constexpr int LFWD_THREADS = 512;
+
 template <bool W_SMEM>
-__global__ void __launch_bounds__(LTHREADS, 1)
+__global__ void __launch_bounds__(LFWD_THREADS, 1)
 lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hid, const float* __restrict__ peep,
                     const float* __restrict__ cell_init, const float* __restrict__ hid_init,
                     const uint8_t* __restrict__ mask, float* __restrict__ out, float* __restrict__ gates,
@@ -197,25 +204,29 @@ lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hi
 
   extern __shared__ __align__(16) float smem[];
   float* hT = smem;                                    // [2][Hpad][LNT]
-  float* Ws = smem + 2 * (size_t)Hpad * LNT;           // [H][128]  (only if W_SMEM)
+  float* xch = smem + 2 * (size_t)Hpad * LNT;          // [512][8] partial-sum exchange
+  float* Ws = xch + LFWD_THREADS * 8;                  // [H][128]  (only if W_SMEM)
 
-  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int tid = threadIdx.x;
+  const int grp = tid >> 8;                            // K-group 0/1
+  const int t8 = tid & 255;
+  const int w = t8 >> 5, l = t8 & 31;
   const int ul = (w & 3) * 8 + (l & 7);                // local unit 0..31
-  const int n0 = ((w >> 2) * 4 + (l >> 3)) * 4;        // first of 4 local utterances
+  const int n0 = ((w >> 2) * 4 + (l >> 3)) * 4;        // first of the 4 local utterances of the matmul tile
   const int ug = rank * LU + ul;                       // global unit
   const bool u_ok = ug < H;
-  const int col0 = rank * 4 * LU;                      // first interleaved column of this CTA
+  const int col0 = rank * 4 * LU;
+  const int nf = n0 + 2 * grp;                         // the 2 utterances this thread finalises: nf, nf+1
 
   if (W_SMEM) {
-    // slice [H][128] of the interleaved W_hid is a contiguous 512-byte run per row
-    for (int i = tid; i < H * 32; i += LTHREADS) {
+    for (int i = tid; i < H * 32; i += LFWD_THREADS) {
       int k = i >> 5, c4 = (i & 31) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (col0 + c4 < H4) v = *reinterpret_cast<const float4*>(w_hid + (size_t)k * H4 + col0 + c4);
       *reinterpret_cast<float4*>(Ws + (size_t)k * 128 + c4) = v;
     }
   }
-  for (int i = tid; i < Hpad * LNT; i += LTHREADS) {
+  for (int i = tid; i < Hpad * LNT; i += LFWD_THREADS) {
     int k = i / LNT;
     hT[i] = k < H ? hid_init[k] : 0.f;
   }
@@ -223,24 +234,23 @@ lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hi
   const float w_ci = (has_peep && u_ok) ? peep[ug] : 0.f;
   const float w_cf = (has_peep && u_ok) ? peep[H + ug] : 0.f;
   const float w_co = (has_peep && u_ok) ? peep[2 * H + ug] : 0.f;
-  float c_prev[4];
+  float c_prev[2];
+  int ng[2];
+  bool n_ok[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) c_prev[i] = u_ok ? cell_init[ug] : 0.f;
-  int ng[4];
-  bool n_ok[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    ng[i] = tile * LNT + n0 + i;
+  for (int i = 0; i < 2; ++i) {
+    c_prev[i] = u_ok ? cell_init[ug] : 0.f;
+    ng[i] = tile * LNT + nf + i;
     n_ok[i] = ng[i] < N;
   }
   cluster.sync();   // everyone's hT[0] / Ws initialised before any remote write can land
 
   // software pipeline over time: the gate pre-activations (and mask) of step s+1 are fetched while step s computes
-  float4 xn[4];
-  bool mnext[4];
+  float4 xn[2];
+  bool mnext[2];
   auto fetch = [&](int t) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       xn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       mnext[i] = false;
       if (n_ok[i] && u_ok) {
@@ -255,17 +265,19 @@ lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hi
   int cur = 0;
   for (int s = 0; s < T; ++s) {
     const int t = backwards ? (T - 1 - s) : s;
-    float acc[4][4];
-    bool m[4];
+    float4 xg[2];
+    bool m[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[i][0] = xn[i].x; acc[i][1] = xn[i].y; acc[i][2] = xn[i].z; acc[i][3] = xn[i].w;
-      m[i] = mnext[i];
-    }
+    for (int i = 0; i < 2; ++i) { xg[i] = xn[i]; m[i] = mnext[i]; }
     if (s + 1 < T) fetch(backwards ? (T - 2 - s) : (s + 1));
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const float* hcur = hT + (size_t)cur * Hpad * LNT;
 #pragma unroll 4
-    for (int k = 0; k < H; ++k) {
+    for (int k = grp; k < H; k += 2) {
       float4 wv;
       if (W_SMEM) wv = *reinterpret_cast<const float4*>(Ws + (size_t)k * 128 + 4 * ul);
       else wv = u_ok ? __ldg(reinterpret_cast<const float4*>(w_hid + (size_t)k * H4 + 4 * ug)) : make_float4(0, 0, 0, 0);
@@ -279,29 +291,50 @@ lstm_fwd_persistent(const float* __restrict__ xw, const float* __restrict__ w_hi
         acc[i][3] = fmaf(hh[i], wv.w, acc[i][3]);
       }
     }
-    float4 hp4 = *reinterpret_cast<const float4*>(hcur + (size_t)(u_ok ? ug : 0) * LNT + n0);
-    const float hpv[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
-    CellOut r[4];
+    // exchange: I keep utterances (2*grp, 2*grp+1) of my tile and hand the other two to my partner (tid ^ 256).
+    // (selects with static register indices: a runtime index would push the accumulators to local memory)
+    float keep[2][4];
+    {
+      float snd[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      r[i] = lstm_cell_fwd(acc[i][0], acc[i][1], acc[i][2], acc[i][3], c_prev[i], hpv[i], m[i], has_peep, w_ci, w_cf,
-                           w_co);
-      c_prev[i] = r[i].c;
+      for (int j = 0; j < 4; ++j) {
+        keep[0][j] = grp ? acc[2][j] : acc[0][j];
+        keep[1][j] = grp ? acc[3][j] : acc[1][j];
+        snd[0][j] = grp ? acc[0][j] : acc[2][j];
+        snd[1][j] = grp ? acc[1][j] : acc[3][j];
+      }
+      float4* dst = reinterpret_cast<float4*>(xch + (size_t)tid * 8);
+      dst[0] = make_float4(snd[0][0], snd[0][1], snd[0][2], snd[0][3]);
+      dst[1] = make_float4(snd[1][0], snd[1][1], snd[1][2], snd[1][3]);
     }
-    // broadcast the new h of my (4 utterances, 1 unit) to every CTA of the cluster, then arrive on the cluster
+    float2 hp2 = *reinterpret_cast<const float2*>(hcur + (size_t)(u_ok ? ug : 0) * LNT + nf);
+    const float hpv[2] = {hp2.x, hp2.y};
+    __syncthreads();
+    CellOut r[2];
+    {
+      const float4* src = reinterpret_cast<const float4*>(xch + (size_t)(tid ^ 256) * 8);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4 pv = src[i];
+        r[i] = lstm_cell_fwd(keep[i][0] + pv.x + xg[i].x, keep[i][1] + pv.y + xg[i].y, keep[i][2] + pv.z + xg[i].z,
+                             keep[i][3] + pv.w + xg[i].w, c_prev[i], hpv[i], m[i], has_peep, w_ci, w_cf, w_co);
+        c_prev[i] = r[i].c;
+      }
+    }
+    // broadcast the new h of my (2 utterances, 1 unit) to every CTA of the cluster, then arrive on the cluster
     // barrier BEFORE the global stores of this step: the barrier's release then only has to cover the DSMEM writes,
     // and the global stores drain underneath the next step's matmul.
     if (u_ok) {
-      float* mine = hT + (size_t)(cur ^ 1) * Hpad * LNT + (size_t)ug * LNT + n0;
-      const float4 hv = make_float4(r[0].h, r[1].h, r[2].h, r[3].h);
+      float* mine = hT + (size_t)(cur ^ 1) * Hpad * LNT + (size_t)ug * LNT + nf;
+      const float2 hv = make_float2(r[0].h, r[1].h);
       for (int rr = 0; rr < CS; ++rr) {
-        float4* dst = reinterpret_cast<float4*>(cluster.map_shared_rank(mine, rr));
+        float2* dst = reinterpret_cast<float2*>(cluster.map_shared_rank(mine, rr));
         *dst = hv;
       }
     }
     cluster.barrier_arrive();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
       if (n_ok[i] && u_ok) {
         size_t row = (size_t)ng[i] * T + t;
         out[row * ldh + ug] = r[i].h;
@@ -513,12 +546,12 @@ __global__ void transpose_pad_kernel(const float* __restrict__ src, int rows, in
 }
 
 template <typename K>
-static int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t st, void** args) {
+static int launch_cluster(K kernel, int grid, int cs, size_t smem, cudaStream_t st, void** args, int threads = LTHREADS) {
   IPAVSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (cs > 8) IPAVSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(LTHREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -569,13 +602,13 @@ int ipavsr_lstm_fwd(const float* xw, const float* w_hid, const float* peep, cons
   if (impl == 0 && cs > 16) impl = 1;
   if (impl == 0) {
     const int tiles = (N + LNT - 1) / LNT;
-    const size_t h_bytes = 2 * (size_t)cs * LU * LNT * sizeof(float);
+    const size_t h_bytes = (2 * (size_t)cs * LU * LNT + LFWD_THREADS * 8) * sizeof(float);
     const size_t w_bytes = (size_t)H * 128 * sizeof(float);
     const bool w_smem = h_bytes + w_bytes <= (size_t)max_smem_optin();
     size_t smem = h_bytes + (w_smem ? w_bytes : 0);
     void* args[] = {&xw, &w_hid, &peep, &cell_init, &hid_init, &mask, &out, &gates, &cell, &hprev, &N, &T, &H, &ldh, &backwards};
-    if (w_smem) return launch_cluster(lstm_fwd_persistent<true>, tiles * cs, cs, smem, st, args);
-    return launch_cluster(lstm_fwd_persistent<false>, tiles * cs, cs, smem, st, args);
+    if (w_smem) return launch_cluster(lstm_fwd_persistent<true>, tiles * cs, cs, smem, st, args, LFWD_THREADS);
+    return launch_cluster(lstm_fwd_persistent<false>, tiles * cs, cs, smem, st, args, LFWD_THREADS);
   }
   // ---- impl 1 ----
   IPAVSR_CHECK_ARG(workspace && workspace_bytes >= ipavsr_lstm_workspace_bytes(N, T, H), "workspace too small");
