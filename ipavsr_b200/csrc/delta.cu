@@ -13,6 +13,7 @@
 // EXACT=true reproduces the reference's float64 operation sequence bit for bit (correctly rounded quotient, float64
 // add, float32 round per theta; FP64-pipe bound); EXACT=false is a plain float32 FMA chain (few-ulp deviation, stated
 // in DESIGN.md; HBM bound).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ipavsr {
@@ -247,6 +248,187 @@ static int dispatch_delta_col(const float* x, int ldx, float* y, int ldy, int N,
   return launch_delta_col<TH, 48, EXACT>(x, ldx, y, ldy, N, T, F, st);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bulk-copy kernel (the streaming path for large batches).  One utterance = one contiguous (T x ldx) input tile and
+// one contiguous (T x ldy) output tile, so both directions are single TMA bulk copies (cp.async.bulk): a persistent
+// CTA keeps a 3-deep ring of input tiles in flight (mbarrier complete_tx) and double-buffers the output tile, whose
+// store is issued by one thread and drains asynchronously (bulk_group) while the next utterance is computed.  The
+// arithmetic is the same register sliding window over the shared tile as in the general kernel.  Nothing but TMA
+// touches global memory: every byte moves in full, aligned, coalesced lines.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DB_THREADS = 256;
+constexpr int DB_STAGES = 3;
+constexpr int DB_RUN = 8;
+
+__device__ __forceinline__ uint32_t db_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void db_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DB_DONE;\n"
+      "bra DB_WAIT;\n"
+      "DB_DONE:\n"
+      "}\n" ::"r"(db_smem(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void db_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(db_smem(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   db_smem(dst)),
+               "l"(src), "r"(bytes), "r"(db_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void db_store(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(db_smem(src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <int TH, bool EXACT>
+__device__ __forceinline__ void db_pass(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int T,
+                                        int F, int tid) {
+  const int runs = (T + DB_RUN - 1) / DB_RUN;
+  const int items = runs * F;
+  for (int it = tid; it < items; it += DB_THREADS) {
+    const int f = it % F;
+    const int t0 = (it / F) * DB_RUN;
+    float w[2 * TH + DB_RUN];
+#pragma unroll
+    for (int i = 0; i < 2 * TH + DB_RUN; ++i) {
+      int t = min(max(t0 - TH + i, 0), T - 1);
+      w[i] = src[t * lds + f];
+    }
+#pragma unroll
+    for (int r = 0; r < DB_RUN; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int th = 1; th <= TH; ++th) acc = delta_step<EXACT>(acc, w[r + TH + th] - w[r + TH - th], th);
+      if (t0 + r < T) dst[(t0 + r) * ldd + f] = acc;
+    }
+  }
+}
+
+// fast (float32) mode, two adjacent features per thread with Blackwell's packed FFMA2:
+//   acc += c*x[t+th];  acc -= c*x[t-th]   (2 packed FMAs per theta for 2 features; 64-bit shared loads)
+template <int TH, int DB_RUN_X2>
+__device__ __forceinline__ void db_pass_x2(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd,
+                                           int T, int F, int tid) {
+  const int runs = (T + DB_RUN_X2 - 1) / DB_RUN_X2;
+  const int F2 = F >> 1;
+  const int items = runs * F2;
+  for (int it = tid; it < items; it += DB_THREADS) {
+    const int f = 2 * (it % F2);
+    const int t0 = (it / F2) * DB_RUN_X2;
+    float2 w[2 * TH + DB_RUN_X2];
+#pragma unroll
+    for (int i = 0; i < 2 * TH + DB_RUN_X2; ++i) {
+      int t = min(max(t0 - TH + i, 0), T - 1);
+      w[i] = *reinterpret_cast<const float2*>(src + t * lds + f);
+    }
+#pragma unroll
+    for (int r = 0; r < DB_RUN_X2; ++r) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int th = 1; th <= TH; ++th) {
+        const float c = 1.0f / (2.0f * (float)th);
+        acc = __ffma2_rn(w[r + TH + th], make_float2(c, c), acc);
+        acc = __ffma2_rn(w[r + TH - th], make_float2(-c, -c), acc);
+      }
+      if (t0 + r < T) *reinterpret_cast<float2*>(dst + (t0 + r) * ldd + f) = acc;
+    }
+  }
+}
+
+template <int TH, bool EXACT, bool X2>
+__global__ void __launch_bounds__(DB_THREADS) delta_fwd_bulk_kernel(const float* __restrict__ x, int ldx,
+                                                                    float* __restrict__ y, int ldy, int N, int T, int F) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ __align__(8) uint64_t full[DB_STAGES];
+  const int in_f = T * ldx, out_f = T * ldy;          // floats per tile (multiples of 4)
+  float* sin = sm;                                     // [DB_STAGES][in_f]
+  float* sout = sm + (size_t)DB_STAGES * in_f;         // [2][out_f]
+  const int tid = threadIdx.x;
+  const uint32_t in_bytes = (uint32_t)in_f * 4, out_bytes = (uint32_t)out_f * 4;
+  if (tid == 0) {
+    for (int s = 0; s < DB_STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(db_smem(&full[s])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // padding columns of the output tiles are written once (zeros) and never touched again
+  for (int i = tid; i < 2 * out_f; i += DB_THREADS) sout[i] = 0.f;
+  __syncthreads();
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_count = first < N ? (N - first + stride - 1) / stride : 0;
+  if (tid == 0)
+    for (int i = 0; i < DB_STAGES && i < my_count; ++i)
+      db_load(sin + (size_t)i * in_f, x + (size_t)(first + (size_t)i * stride) * in_f, in_bytes, &full[i]);
+  for (int i = 0; i < my_count; ++i) {
+    const int stage = i % DB_STAGES;
+    const uint32_t phase = (uint32_t)(i / DB_STAGES) & 1u;
+    const int n = first + i * stride;
+    float* so = sout + (size_t)(i & 1) * out_f;
+    const float* si = sin + (size_t)stage * in_f;
+    // the bulk store that last read this output buffer (utterance i-2) must have finished reading shared memory
+    if (tid == 0 && i >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    db_mbar_wait(&full[stage], phase);
+    __syncthreads();
+    // x block and d block
+    for (int j = tid; j < T * F; j += DB_THREADS) {
+      const int t = j / F, f = j - t * F;
+      so[t * ldy + f] = si[t * ldx + f];
+    }
+    // short runs when there would otherwise be too few (feature pair, run) items for the 256 threads
+    const bool short_runs = ((T + DB_RUN - 1) / DB_RUN) * (F >> 1) < 100;
+    if (X2) {
+      if (short_runs) db_pass_x2<TH, 4>(si, ldx, so + F, ldy, T, F, tid);
+      else db_pass_x2<TH, 8>(si, ldx, so + F, ldy, T, F, tid);
+    }
+    else db_pass<TH, EXACT>(si, ldx, so + F, ldy, T, F, tid);
+    __syncthreads();
+    // the input stage is free again: prefetch utterance i + DB_STAGES into it
+    if (tid == 0 && i + DB_STAGES < my_count)
+      db_load(sin + (size_t)stage * in_f, x + (size_t)(first + (size_t)(i + DB_STAGES) * stride) * in_f, in_bytes,
+              &full[stage]);
+    if (X2) {
+      if (short_runs) db_pass_x2<TH, 4>(so + F, ldy, so + 2 * F, ldy, T, F, tid);
+      else db_pass_x2<TH, 8>(so + F, ldy, so + 2 * F, ldy, T, F, tid);
+    }
+    else db_pass<TH, EXACT>(so + F, ldy, so + 2 * F, ldy, T, F, tid);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) db_store(y + (size_t)n * out_f, so, out_bytes);
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int TH, bool EXACT, bool X2>
+static int launch_delta_bulk_k(const float* x, int ldx, float* y, int ldy, int N, int T, int F, cudaStream_t st);
+
+template <int TH, bool EXACT>
+static int launch_delta_bulk(const float* x, int ldx, float* y, int ldy, int N, int T, int F, cudaStream_t st) {
+  // packed two-feature path: float32 mode, even F (so that F, 2F and every row start are 8-byte aligned)
+  if (!EXACT && F % 2 == 0) return launch_delta_bulk_k<TH, false, true>(x, ldx, y, ldy, N, T, F, st);
+  return launch_delta_bulk_k<TH, EXACT, false>(x, ldx, y, ldy, N, T, F, st);
+}
+
+template <int TH, bool EXACT, bool X2>
+static int launch_delta_bulk_k(const float* x, int ldx, float* y, int ldy, int N, int T, int F, cudaStream_t st) {
+  const size_t smem = ((size_t)DB_STAGES * T * ldx + (size_t)2 * T * ldy) * sizeof(float);
+  auto k = delta_fwd_bulk_kernel<TH, EXACT, X2>;
+  IPAVSR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((220 * 1024) / (smem + 2048));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 6) per_sm = 6;
+  int grid = sm_count() * per_sm;
+  if (grid > N) grid = N;
+  k<<<grid, DB_THREADS, smem, st>>>(x, ldx, y, ldy, N, T, F);
+  IPAVSR_LAUNCH_CHECK();
+  return IPAVSR_OK;
+}
+
 template <int TH, bool EXACT>
 static int launch_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, int T, int F, int theta, int upc,
                             int grid, size_t smem, cudaStream_t st) {
@@ -269,7 +451,27 @@ int ipavsr_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, int T, i
   IPAVSR_CHECK_ARG(ldx >= F && ldy >= 3 * F, "leading dimensions too small");
   if (N == 0) return IPAVSR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (T <= 48 && (theta == 1 || theta == 4 || theta == 9)) {
+  const bool tiles_ok = (ldx % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                        ((size_t)DB_STAGES * T * ldx + (size_t)2 * T * ldy) * sizeof(float) <= 200 * 1024;
+  static int force_path = -1;   // IPAVSR_DELTA_PATH=bulk|col|general (benchmarking aid); default: automatic
+  if (force_path < 0) {
+    const char* e = getenv("IPAVSR_DELTA_PATH");
+    force_path = !e ? 0 : (e[0] == 'b' ? 1 : (e[0] == 'c' ? 2 : 3));
+  }
+  // exact mode with a wide window is FP64-pipe bound: the register-resident column kernel is the faster one there
+  const bool prefer_col = exact && theta >= 4 && T <= 48;
+  if (tiles_ok && (theta == 1 || theta == 4 || theta == 9) && N >= 64 &&
+      ((force_path == 0 && !prefer_col) || force_path == 1)) {
+    // TMA bulk-copy streaming kernel
+    if (theta == 1) return exact ? launch_delta_bulk<1, true>(x, ldx, y, ldy, N, T, F, st)
+                                 : launch_delta_bulk<1, false>(x, ldx, y, ldy, N, T, F, st);
+    if (theta == 4) return exact ? launch_delta_bulk<4, true>(x, ldx, y, ldy, N, T, F, st)
+                                 : launch_delta_bulk<4, false>(x, ldx, y, ldy, N, T, F, st);
+    return exact ? launch_delta_bulk<9, true>(x, ldx, y, ldy, N, T, F, st)
+                 : launch_delta_bulk<9, false>(x, ldx, y, ldy, N, T, F, st);
+  }
+  if (T <= 48 && (theta == 1 || theta == 4 || theta == 9) && force_path != 3) {
     // register-resident column kernel (every shipped configuration: T <= 40, theta = 9)
     if (theta == 1) return exact ? dispatch_delta_col<1, true>(x, ldx, y, ldy, N, T, F, st)
                                  : dispatch_delta_col<1, false>(x, ldx, y, ldy, N, T, F, st);

@@ -21,7 +21,7 @@ def _train(name, rank, world, steps, q=None, port=None):
     from ipavsr_b200.engine import get_engine
     from ipavsr_b200.function import function, tensor as T
     from ipavsr_b200.custom.objectives import temporal_softmax_loss, categorical_crossentropy
-    from ipavsr_b200.custom.updates import adam
+    from ipavsr_b200.custom.updates import nesterov_momentum
     if world > 1:
         os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                           LOCAL_RANK=str(rank))
@@ -43,7 +43,7 @@ def _train(name, rank, world, steps, q=None, port=None):
     params = L.get_all_params(net, trainable=True)
     order = [ins[n].input_var for n in spec['names']]
     train = function([order[0], targets, ins['mask'].input_var] + order[1:] + [T.iscalar('w')], cost,
-                     updates=adam(cost, params, learning_rate=1e-2))
+                     updates=nesterov_momentum(cost, params, learning_rate=5e-2, momentum=0.9))
     if world > 1:
         parallel.attach(train.engine)
     lo, hi = parallel.shard_bounds(N, rank, world)
@@ -82,6 +82,7 @@ def test_two_gpu_training_matches_single_gpu(name):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    # SGD-type rule on purpose: Adam's g/sqrt(v) turns summation-order noise of near-zero gradients into O(lr) moves
     np.testing.assert_allclose(losses, ref_losses, rtol=2e-4)
     for a, b in zip(vals, ref_vals):
-        assert np.abs(a - b).max() < 5e-4 * max(1.0, np.abs(b).max())
+        assert np.abs(a - b).max() < 2e-5 * max(1.0, np.abs(b).max())

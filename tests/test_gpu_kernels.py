@@ -57,7 +57,8 @@ def test_gemm_strided_views():
 # DeltaLayer
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('N,T,F,theta', [(2, 3, 5, 1), (26, 40, 50, 9), (7, 29, 90, 9), (5, 40, 30, 4), (3, 17, 50, 6),
-                                         (1, 1, 4, 3), (300, 40, 50, 9), (4, 12, 51, 2)])
+                                         (1, 1, 4, 3), (300, 40, 50, 9), (4, 12, 51, 2), (1000, 40, 90, 9), (777, 29, 30, 4),
+                                         (130, 48, 50, 1), (70, 60, 20, 9)])
 def test_delta_fwd_exact(N, T, F, theta):
     rng = np.random.default_rng(N + T + F + theta)
     x = rng.normal(size=(N, T, F)).astype('float32')
