@@ -157,7 +157,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--batch', type=int, default=512, help='utterances per GPU per step')
-    ap.add_argument('--mode', default=os.environ.get('IPAVSR_GEMM_MODE', 'fp32'))
+    ap.add_argument('--mode', default=os.environ.get('IPAVSR_GEMM_MODE', 'tf32x3'),
+                    help='GEMM arithmetic: tf32x3 (fp32-parity, default) | fp32 (CUDA cores) | tf32 (single pass)')
     ap.add_argument('--cpu-sample', type=int, default=26)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
@@ -252,6 +253,10 @@ def main():
     ms_e2e, _ = timed(step_e2e, args.steps, 3)
     value = args.batch * world / (ms_dev * 1e-3)
     e2e = args.batch * world / (ms_e2e * 1e-3)
+    # forward-only (deterministic) pass of the same network: frames/s
+    val_fn = function([v[0], v[1], v[2], mask_var, window], L.get_output(net, deterministic=True))
+    ms_fwd, _ = timed(lambda: val_fn(dx[0], dx[1], dx[2], dmask, THETA), max(3, args.steps // 2), 3)
+    fwd_frames = args.batch * world * T_FRAMES / (ms_fwd * 1e-3)
     h2d = sum(int(h.numel() * h.element_size()) for h in hx) + int(hmask.numel()) + int(hy.numel() * 4)
 
     # ---- roofline of the dominant kernel: the fc1 encoder GEMM (M = batch*T rows, K=1200, N=2000) ----
@@ -264,12 +269,19 @@ def main():
         Cm = torch.empty(M, N, device='cuda')
         bias = torch.zeros(N, device='cuda')
         mode = {'fp32': 0, 'tf32x3': 1, 'tf32': 2}[args.mode]
-        need = lib.ipavsr_gemm_workspace_bytes(mode, 0, 0, M, N, K)
-        ws = torch.empty(max(int(need) // 4, 4), device='cuda')
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         flush = torch.empty(192 * 1024 * 1024 // 4, device='cuda')
-        run = lambda: _lib.call('ipavsr_gemm', mode, 0, 0, M, N, K, A.data_ptr(), K, B.data_ptr(), N, Cm.data_ptr(), N,
-                                bias.data_ptr(), 1, 0, ws.data_ptr(), int(need), st)
+        if mode == 1:
+            # inside the step the operands arrive already split (weights once per step, activations by the producing
+            # epilogue), so the dominant kernel is the presplit 3xTF32 tcgen05 GEMM
+            ah, al, bh, bl = torch.empty_like(A), torch.empty_like(A), torch.empty_like(B), torch.empty_like(B)
+            _lib.call('ipavsr_tf32_split_rna', A.data_ptr(), ah.data_ptr(), al.data_ptr(), A.numel(), st)
+            _lib.call('ipavsr_tf32_split_rna', B.data_ptr(), bh.data_ptr(), bl.data_ptr(), B.numel(), st)
+            run = lambda: _lib.call('ipavsr_gemm_tf32x3_presplit', 0, 0, M, N, K, ah.data_ptr(), al.data_ptr(), K,
+                                    bh.data_ptr(), bl.data_ptr(), N, Cm.data_ptr(), N, bias.data_ptr(), 1, 0, None, None, st)
+        else:
+            run = lambda: _lib.call('ipavsr_gemm', mode, 0, 0, M, N, K, A.data_ptr(), K, B.data_ptr(), N, Cm.data_ptr(), N,
+                                    bias.data_ptr(), 1, 0, None, 0, st)
         for _ in range(3):
             run()
         tot = 0.0
@@ -290,8 +302,15 @@ def main():
             pass
         peak = float(peaks.get('bf16_tflops', 1590.0))
         achieved = 2.0 * M * N * K / (gemm_ms * 1e-3) / 1e12
-        roofline = {'bound': 'tensor', 'kernel': 'encoder fc1 GEMM %dx%dx%d (%s)' % (M, N, K, args.mode),
-                    'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, 'profiles', 'r01_dominant_kernel.json')))
+            if prof.get('mode') == args.mode and prof.get('shape') == [M, N, K]:
+                traffic = prof.get('dram_bytes_per_launch')
+        except Exception:
+            pass
+        roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel: encoder fc1 GEMM %dx%dx%d (%s)' % (M, N, K, args.mode),
+                    'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                     'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback 1.59 PFLOP/s',
                     'note': 'algorithmic FLOPs; fp32 parity on tf32 tensor cores costs 3 MMAs/product and tf32 peak is '
                             'half of bf16, so the ceiling of this mode is 1/6 of the bf16 peak',
@@ -309,7 +328,8 @@ def main():
                 'e2e': {'value': e2e, 'unit': 'utterances/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                         'ms_per_step': ms_e2e},
                 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-                'model_tflops': flops_per_utt_train() * args.batch * world / (ms_dev * 1e-3) / 1e12}
+                'model_tflops': flops_per_utt_train() * args.batch * world / (ms_dev * 1e-3) / 1e12,
+                'fwd_frames_per_s': fwd_frames, 'fwd_ms_per_batch': ms_fwd}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

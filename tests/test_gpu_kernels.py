@@ -458,3 +458,24 @@ def test_preprocessing_large_properties():
     np.testing.assert_array_equal(dd[:, 0], dd[:, 1])
     # oracle on a slice
     np.testing.assert_allclose(y[:64], OP.normalize_input(X[:64]), rtol=3e-6, atol=3e-6)
+
+
+def test_preprocessing_python_api_matches_reference_golden():
+    """The reference-named Python functions (ipavsr_b200.utils.preprocessing) against the reference's own outputs."""
+    from ipavsr_b200.utils import preprocessing as P, signal as S
+    X, lens = GOLD['X'], GOLD['lens']
+    np.testing.assert_allclose(P.normalize_input(X.copy()), GOLD['normalize_input'], rtol=2e-6, atol=2e-6)
+    n, m, s = P.featurewise_normalize_sequence(X)
+    np.testing.assert_allclose(n, GOLD['featurewise_norm'], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(m, GOLD['featurewise_mean'], rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(P.sequencewise_mean_image_subtraction(X, lens), GOLD['seq_mean_sub'])
+    np.testing.assert_array_equal(P.compute_diff_images(X, lens), GOLD['diff_images'])
+    np.testing.assert_allclose(P.concat_first_second_deltas(GOLD['Xd'], lens, 9), GOLD['concat_deltas_w9'], rtol=1e-12,
+                               atol=1e-10)
+    np.testing.assert_allclose(P.deltas(GOLD['test_delta_in'], 9), GOLD['test_delta_out'], atol=1e-9)
+    np.testing.assert_allclose(P.deltas(GOLD['leftpad_in'], 9), GOLD['leftpad_out'], atol=1e-9)
+    with pytest.raises(IndexError):
+        P.compute_diff_images(X[:3], [1, 2])
+    seqs = np.array([[[1, 2, 3, 4, 5], [10, 12, 13, 14, 15], [300, 1, 23, 56, 22]]], dtype='float32')
+    np.testing.assert_array_equal(S.append_delta_coeff(seqs[0], 1)[0],
+                                  [1, 2, 3, 4, 5, 4.5, 5, 5, 5, 5, 72.5, -2.75, 2.5, 10.5, 1.75])
