@@ -816,7 +816,7 @@ class Engine(object):
         else:
             _lib.call('ipavsr_categorical_crossentropy', p.ptr, p.ld, yd.data_ptr(), buf.data_ptr(), None, 0, p.rows,
                       p.cols, 1.0, None, st)
-            both = torch.stack([buf[0], torch.tensor(float(p.rows), device=self.device)])
+            both = torch.stack([buf[0], torch.tensor(float(p.rows), dtype=torch.float32, device=self.device)])
         if self.world is not None:
             torch.distributed.all_reduce(both, group=self.world[2])
         h = both.cpu().numpy()

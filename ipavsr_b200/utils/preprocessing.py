@@ -46,7 +46,8 @@ def featurewise_normalize_sequence(input):
     """`utils/preprocessing.py:245-257`: returns (normalised, feature_means, feature_std)."""
     x = _dev(input)
     frames, F = x.shape
-    mean, std = torch.empty(F, device='cuda'), torch.empty(F, device='cuda')
+    mean = torch.empty(F, dtype=torch.float32, device='cuda')
+    std = torch.empty(F, dtype=torch.float32, device='cuda')
     scratch = torch.empty(3 * F, dtype=torch.float64, device='cuda')
     _lib.call('ipavsr_norm_featurewise_stats', x.data_ptr(), F, mean.data_ptr(), std.data_ptr(), scratch.data_ptr(),
               frames, F, _st())

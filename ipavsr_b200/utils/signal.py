@@ -18,7 +18,7 @@ def append_delta_coeff(A, theta, exact=True):
     xp = np.zeros((N * T, ldx), np.float32)
     xp[:, :F] = a.reshape(N * T, F)
     x = torch.from_numpy(xp).cuda()
-    y = torch.zeros(N * T, ldy, device='cuda')
+    y = torch.zeros(N * T, ldy, dtype=torch.float32, device='cuda')
     _lib.call('ipavsr_delta_fwd', x.data_ptr(), ldx, y.data_ptr(), ldy, N, T, F, int(theta), 1 if exact else 0,
               C.c_void_p(torch.cuda.current_stream().cuda_stream))
     out = y.cpu().numpy()[:, :3 * F].reshape(N, T, 3 * F)

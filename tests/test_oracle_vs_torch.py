@@ -7,7 +7,15 @@ import torch
 from oracle import ops
 import torch_ref as R
 
-torch.set_default_dtype(torch.float64)
+
+
+@pytest.fixture(autouse=True)
+def _float64_default():
+    """torch_ref builds float64 graphs; restore the default afterwards so that no other test module inherits it."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
 
 
 def _t(a, grad=True):

@@ -133,7 +133,10 @@ if 'gemm' in only:
             report('gemm %-18s %dx%dx%d %s' % (name, M, N, K, label), ms, flops=fl)
         del A, B, Cm, ah, al, bh, bl
 if 'lstm' in only:
-    for N, H, I in ((26, 250, 150), (512, 250, 150), (512, 250, 750), (512, 500, 150), (4096, 250, 150)):
+    shapes = ((26, 250, 150), (512, 250, 150), (512, 500, 150), (4096, 250, 150))
+    if os.environ.get('IPAVSR_BENCH_LSTM_N'):
+        shapes = tuple((int(n), 250, 150) for n in os.environ['IPAVSR_BENCH_LSTM_N'].split(','))
+    for N, H, I in shapes:
         ldh = (H + 3) // 4 * 4
         xw = torch.randn(N * T, 4 * H, device='cuda')
         whid = torch.randn(H, 4 * H, device='cuda') * 0.05
