@@ -44,6 +44,7 @@ extern "C" {
 #define IPAVSR_GEMM_TF32X3 1    /* tcgen05 kind::tf32, 3-term error-compensated split (fp32 parity)  */
 #define IPAVSR_GEMM_TF32 2      /* tcgen05 kind::tf32, single pass (states its own tolerance)        */
 #define IPAVSR_GEMM_BF16X3 3    /* reserved */
+#define IPAVSR_GEMM_F16X3 4     /* tcgen05 kind::f16, 3-term split on fp16 hi/lo + per-tensor scale (fp32 parity) */
 
 /* optimiser kinds (reference custom/updates.py:35-99; lasagne.updates adam/adadelta/sgd/momentum) */
 #define IPAVSR_OPT_ADAM 0
@@ -80,6 +81,25 @@ int ipavsr_tf32_split_rna(const float* x, float* hi, float* lo, uint64_t n, void
 int ipavsr_gemm_tf32x3_presplit(int transA, int transB, int M, int N, int K, const float* A_hi, const float* A_lo,
                                 int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
                                 const float* bias, int act, int accumulate, float* C_hi, float* C_lo, void* stream);
+
+/* ---- fp16 three-product mode (IPAVSR_GEMM_F16X3): x * 2^e = hi + lo * 2^-11, hi/lo fp16, e per tensor ---------
+ * Same accuracy as the 3xTF32 mode at twice the MMA rate and half the operand bytes.  `amax` (device float) holds the
+ * tensor's max |x|: accumulated by the call (amax_ready=0) or by the producing kernel (amax_ready=1; the GEMM epilogue
+ * and ipavsr_amax do `atomic max`, so zero it first).  hi/lo are fp16 arrays with leading dimension ldo (halves,
+ * a multiple of 8 for TMA); exp_out (device int32) receives e. */
+int ipavsr_amax(const float* x, int ldx, int64_t rows, int cols, float* amax, void* stream);
+int ipavsr_f16_split(const float* x, int ldx, int64_t rows, int cols, uint16_t* hi, uint16_t* lo, int ldo, float* amax,
+                     int32_t* exp_out, int amax_ready, void* stream);
+/* the whole flat parameter arena at once: seg_id maps every 256-float block to its tensor (NULL: one tensor);
+ * amax / exps have nseg entries */
+int ipavsr_f16_split_segments(const float* x, uint16_t* hi, uint16_t* lo, uint64_t n, const int32_t* seg_id, int nseg,
+                              float* amax, int32_t* exps, void* stream);
+/* C = act(op(A) op(B) (+C) + bias) on split operands (lda/ldb in halves); amax_out (optional) receives max |C| */
+int ipavsr_gemm_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* A_hi, const uint16_t* A_lo, int lda,
+                      const int32_t* expA, const uint16_t* B_hi, const uint16_t* B_lo, int ldb, const int32_t* expB,
+                      float* C, int ldc, const float* bias, int act, int accumulate, float* amax_out, void* stream);
+/* 1 if the fp16 tensor-core path takes this product (16-byte aligned hi/lo, ld % 8 == 0, K >= 16, N >= 8, >= 4 MFLOP) */
+int ipavsr_gemm_f16_supported(int M, int N, int K, const void* A, int lda, const void* B, int ldb);
 
 /* dZ = dY * act'(Y)  and  db[N] (+)= column sums of dZ   (backward of DenseLayer's nonlinearity and bias).
  * dZ may alias dY.  db may be NULL. */

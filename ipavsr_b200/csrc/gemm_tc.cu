@@ -13,6 +13,11 @@
 //   warp 2  TMEM allocator tcgen05.alloc / dealloc of BN columns
 //   warps 4-7 epilogue     tcgen05.ld 32x32b (one TMEM lane = one output row per thread), bias + activation,
 //                          vectorised global stores (or float atomics for split-K)
+// IPAVSR_GEMM_F16X3 is the same three-product scheme on 16-bit operands (kind::f16, twice the MMA rate and half the
+// operand bytes of tf32): x * 2^e = hi + lo * 2^-11 with hi, lo in fp16 and e a per-tensor power-of-two scale chosen
+// from the tensor's amax (f16split.cu); hi*hi goes to the main accumulators, lo*hi + hi*lo to the cross accumulator,
+// and the epilogue forms (main + cross * 2^-11) * 2^-(eA+eB).
+//
 // Operand layouts: a K-major operand (reduction dim contiguous) is one TMA box of [rows x 32 floats]; an MN-major
 // operand (stored transposed: A as [K,M] for wgrad, B as [K,N] for the forward x*W) is BLOCK/32 boxes of
 // [32 k-rows x 32 floats] (TMA swizzle 128B_ATOM_32B) and is consumed through MN-major UMMA descriptors
@@ -23,7 +28,7 @@
 namespace ipavsr {
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                 // floats per stage along K (one 128-byte swizzle row)
+constexpr int TC_BK = 32;                 // floats per stage along K (one 128-byte swizzle row); 64 halves in f16 mode
 constexpr int TC_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -72,6 +77,17 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -115,10 +131,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-// instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+// instruction descriptor: D=f32, A=B=tf32 (format 2, kind::tf32) or fp16 (format 0, kind::f16), majors, N>>3, M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, bool f16) {
+  return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
 struct TcParams {
@@ -132,18 +148,25 @@ struct TcParams {
   int splits;
   float* Chi;         // optional: rna_tf32(C) and rna_tf32(C - Chi), same ldc (operands of a following 3xTF32 GEMM)
   float* Clo;
+  const int32_t* expA;   // f16 mode: per-tensor scale exponents of the operands (device), result *= 2^-(eA+eB)
+  const int32_t* expB;
+  float* amax;           // optional (device): atomic max of |C| over the written elements (feeds the next fp16 split)
 };
 
-template <int BN, bool A_MN, bool B_MN, int NPROD>
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, TcParams p) {
+  constexpr int BKE = F16 ? 2 * TC_BK : TC_BK;        // elements per stage along K (128 bytes either way)
+  constexpr int MNBOX = F16 ? 64 : 32;                // MN-major TMA box: 128 bytes of M/N x BKE k-rows
+  constexpr int MNBOX_BYTES = BKE * 128;
   constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
   constexpr int B_BYTES = BN * TC_BK * 4;
   constexpr int NOPER = (NPROD == 3) ? 2 : 1;         // hi (+ lo) copies of each operand
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
   constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
   static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(!F16 || NPROD == 3, "the fp16 path is the three-product mode");
   // TMEM accumulators.  The tensor core adds into its fp32 accumulator with truncation, so the error grows with the
   // number of accumulations into one accumulator.  In the 3xTF32 mode the tiny cross terms (lo*hi + hi*lo) get their
   // own accumulator and the hi*hi terms are spread round-robin (by k-block) over NMAIN accumulators; the epilogue sums
@@ -158,7 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int num_kb_total = (p.K + TC_BK - 1) / TC_BK;
+  const int num_kb_total = (p.K + BKE - 1) / BKE;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
   const int num_kb = max(kb_end - kb_begin, 0);
@@ -191,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
       uint8_t* sB = sA + NOPER * A_BYTES;
       mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-      const int k0 = (kb_begin + kb) * TC_BK;
+      const int k0 = (kb_begin + kb) * BKE;
 #pragma unroll
       for (int o = 0; o < NOPER; ++o) {
         const CUtensorMap* ma = o == 0 ? &mapA : &mapAlo;
@@ -200,22 +223,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tma_load_2d(sA + o * A_BYTES, ma, &full_bar[stage], k0, m0);                 // box {32 k, 128 rows}
         } else {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 32; ++j)                                         // boxes {32 m, 32 k-rows}
-            tma_load_2d(sA + o * A_BYTES + j * 4096, ma, &full_bar[stage], m0 + 32 * j, k0);
+          for (int j = 0; j < TC_BM / MNBOX; ++j)                                      // boxes {128 B of m, BKE k-rows}
+            tma_load_2d(sA + o * A_BYTES + j * MNBOX_BYTES, ma, &full_bar[stage], m0 + MNBOX * j, k0);
         }
         if (!B_MN) {
           tma_load_2d(sB + o * B_BYTES, mb, &full_bar[stage], k0, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            tma_load_2d(sB + o * B_BYTES + j * 4096, mb, &full_bar[stage], n0 + 32 * j, k0);
+          for (int j = 0; j < BN / MNBOX; ++j)
+            tma_load_2d(sB + o * B_BYTES + j * MNBOX_BYTES, mb, &full_bar[stage], n0 + MNBOX * j, k0);
         }
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN, F16);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
@@ -228,11 +251,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // K-major (SWIZZLE_128B): advance 32 bytes inside the swizzled 128-byte row; SBO = 1024 (8 rows).
         // MN-major (SWIZZLE_128B_BASE32B, atoms of 4 k-rows x 128 bytes): advance 8 k-rows (1024 bytes);
         // SBO = 512 (next 4-row atom along K), LBO = 4096 (next 32-wide chunk along M/N = next TMA box).
-        const uint32_t a_off = A_MN ? k * 1024 : k * 32;
-        const uint32_t b_off = B_MN ? k * 1024 : k * 32;
-        const uint32_t a_lbo = A_MN ? 4096 : 16, b_lbo = B_MN ? 4096 : 16;
-        const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
-        const uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
+        // fp16 MN-major is the plain SWIZZLE_128B canonical layout: atoms of 8 k-rows x 128 bytes (64 halves of M/N),
+        // one MMA (K = 16) spans two atoms: advance 2048 bytes, SBO = 1024 (next atom along K), LBO = next TMA box.
+        constexpr uint32_t MN_STEP = F16 ? 2048 : 1024, MN_SBO = F16 ? 1024 : 512, MN_LT = F16 ? 2 : 1;
+        const uint32_t a_off = A_MN ? k * MN_STEP : k * 32;
+        const uint32_t b_off = B_MN ? k * MN_STEP : k * 32;
+        const uint32_t a_lbo = A_MN ? MNBOX_BYTES : 16, b_lbo = B_MN ? MNBOX_BYTES : 16;
+        const uint32_t a_sbo = A_MN ? MN_SBO : 1024, b_sbo = B_MN ? MN_SBO : 1024;
+        const uint32_t a_lt = A_MN ? MN_LT : 2, b_lt = B_MN ? MN_LT : 2;
         const uint64_t a_hi = make_smem_desc(sA + a_off, a_lbo, a_sbo, a_lt);
         const uint64_t b_hi = make_smem_desc(sB + b_off, b_lbo, b_sbo, b_lt);
         const uint32_t first = (kb | k) == 0 ? 0u : 1u;
@@ -242,9 +268,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t t_cross = tmem_base + (uint32_t)(NMAIN * BN);
           const uint32_t t_main = tmem_base + (uint32_t)((kb % NMAIN) * BN);
           const uint32_t main_acc = (kb < NMAIN && k == 0) ? 0u : 1u;
-          tcgen05_mma_tf32(t_cross, a_lo, b_hi, idesc, first);
-          tcgen05_mma_tf32(t_cross, a_hi, b_lo, idesc, 1u);
-          tcgen05_mma_tf32(t_main, a_hi, b_hi, idesc, main_acc);
+          if (F16) {
+            tcgen05_mma_f16(t_cross, a_lo, b_hi, idesc, first);
+            tcgen05_mma_f16(t_cross, a_hi, b_lo, idesc, 1u);
+            tcgen05_mma_f16(t_main, a_hi, b_hi, idesc, main_acc);
+          } else {
+            tcgen05_mma_tf32(t_cross, a_lo, b_hi, idesc, first);
+            tcgen05_mma_tf32(t_cross, a_hi, b_lo, idesc, 1u);
+            tcgen05_mma_tf32(t_main, a_hi, b_hi, idesc, main_acc);
+          }
         } else {
           tcgen05_mma_tf32(tmem_base, a_hi, b_hi, idesc, first);
         }
@@ -263,6 +295,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     const bool split = p.splits > 1;
     const bool vec = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    float osc1 = 1.f, osc2 = 1.f;                  // f16 mode: result = acc * 2^-(eA+eB), applied as two exact factors
+    if (F16) {
+      const int e = -(__ldg(p.expA) + __ldg(p.expB));
+      const int e1 = e / 2, e2 = e - e1;
+      osc1 = __int_as_float((127 + e1) << 23);
+      osc2 = __int_as_float((127 + e2) << 23);
+    }
+    float tile_max = 0.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.N) break;                   // warp-uniform
@@ -271,6 +311,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         if (NPROD == 3) {
           tmem_ld32(lane_base + (uint32_t)(NMAIN * BN), v);                 // cross terms first (smallest)
+          if (F16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= (1.0f / 2048.0f);          // lo carries a 2^11 scale
+          }
           const int used = num_kb < NMAIN ? num_kb : NMAIN;
 #pragma unroll 1
           for (int a = 0; a < used; ++a) {
@@ -278,6 +322,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tmem_ld32(lane_base + (uint32_t)(a * BN), u);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
+          if (F16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * osc1 * osc2;
           }
         } else {
           tmem_ld32(lane_base, v);
@@ -313,6 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               }
               o.x = act_fwd(o.x, p.act); o.y = act_fwd(o.y, p.act); o.z = act_fwd(o.z, p.act); o.w = act_fwd(o.w, p.act);
               *reinterpret_cast<float4*>(cp + j4) = o;
+              tile_max = fmaxf(tile_max, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
               if (p.Chi != nullptr) {
                 float4 h, l;
                 tf32_hi_lo(o.x, h.x, l.x); tf32_hi_lo(o.y, h.y, l.y); tf32_hi_lo(o.z, h.z, l.z); tf32_hi_lo(o.w, h.w, l.w);
@@ -329,6 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                   if (p.bias != nullptr) o += __ldg(p.bias + col + j);
                   o = act_fwd(o, p.act);
                   cp[j4 + j] = o;
+                  tile_max = fmaxf(tile_max, fabsf(o));
                   if (p.Chi != nullptr) {
                     float h, l;
                     tf32_hi_lo(o, h, l);
@@ -340,6 +390,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       }
+    }
+    if (p.amax != nullptr && !split) {
+      tile_max = warp_max(tile_max);
+      if (lane == 0 && tile_max > 0.f) atomicMax(reinterpret_cast<unsigned int*>(p.amax), __float_as_uint(tile_max));
     }
     tcgen05_fence_before();
   }
@@ -383,21 +437,22 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D row-major fp32 tensor [outer][inner] with row stride ld floats; box {box_inner, box_outer}; 128B swizzle
-static int make_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                    uint32_t box_outer, bool mn_major) {
+// 2-D row-major tensor [outer][inner] (fp32, or fp16 when f16) with row stride ld elements; box {box_inner, box_outer};
+// 128B swizzle (the 32B-atom variant for MN-major 32-bit operands)
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                    uint32_t box_outer, bool mn_major, bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
     set_error("gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
     return IPAVSR_ERR_CUDA;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint64_t strides[1] = {ld * (f16 ? 2 : 4)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   (mn_major && !f16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -432,7 +487,7 @@ uint64_t gemm_tc_workspace_bytes(int mode, int transA, int transB, int M, int N,
   return 2 * (a + b) * sizeof(float) * 2;   // x2 head-room for leading dimensions up to twice the logical width
 }
 
-template <int BN, bool A_MN, bool B_MN, int NPROD>
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo,
                      TcParams p, cudaStream_t st) {
   constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
@@ -440,7 +495,7 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUten
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
   constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD, F16>;
   IPAVSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
   kern<<<grid, TC_THREADS, smem, st>>>(mA, mAlo, mB, mBlo, p);
@@ -448,47 +503,54 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUten
   return IPAVSR_OK;
 }
 
-template <int BN, int NPROD>
+template <int BN, int NPROD, bool F16>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
                           const CUtensorMap& mBlo, TcParams p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD>(mA, mAlo, mB, mBlo, p, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD>(mA, mAlo, mB, mBlo, p, st);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD>(mA, mAlo, mB, mBlo, p, st);
-  return launch_tc<BN, true, true, NPROD>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
+  return launch_tc<BN, true, true, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
 }
 
-// core: operands already split (3xTF32) or raw (TF32: *lo ignored)
-static int gemm_tc_core(bool x3, int transA, int transB, int M, int N, int K, const float* Ahi, const float* Alo, int lda,
-                        const float* Bhi, const float* Blo, int ldb, float* C, int ldc, const float* bias, int act,
-                        int accumulate, float* Chi, float* Clo, cudaStream_t st) {
+int amax_launch(const float* x, int ldx, int rows, int cols, float* amax, cudaStream_t st);   // f16split.cu
+
+// core: operands already split (3xTF32: fp32 hi/lo arrays; f16: fp16 hi/lo arrays + scale exponents) or raw (TF32:
+// *lo ignored).  kind: 0 = single TF32, 1 = 3xTF32, 2 = fp16 three-product.
+static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, const void* Ahi, const void* Alo, int lda,
+                        const void* Bhi, const void* Blo, int ldb, float* C, int ldc, const float* bias, int act,
+                        int accumulate, float* Chi, float* Clo, const int32_t* expA, const int32_t* expB, float* amax,
+                        cudaStream_t st) {
+  const bool x3 = kind != 0, f16 = kind == 2;
   const bool a_mn = transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;     // B stored [K,N]: N contiguous
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int bke = f16 ? 2 * TC_BK : TC_BK;      // elements per k-block = 128 bytes
+  const int mnbox = f16 ? 64 : 32;              // MN-major box: 128 bytes of M/N, bke k-rows
   CUtensorMap mA, mAlo, mB, mBlo;
   int rc;
-  // A: K-major -> tensor [M][K], box {32, 128};  MN-major -> tensor [K][M], box {32, 32}
+  // A: K-major -> tensor [M][K], box {bke, 128};  MN-major -> tensor [K][M], box {mnbox, bke}
   if (!a_mn) {
-    if ((rc = make_map(&mA, Ahi, K, M, lda, TC_BK, TC_BM, false))) return rc;
-    if ((rc = make_map(&mAlo, Alo, K, M, lda, TC_BK, TC_BM, false))) return rc;
+    if ((rc = make_map(&mA, Ahi, K, M, lda, bke, TC_BM, false, f16))) return rc;
+    if ((rc = make_map(&mAlo, Alo, K, M, lda, bke, TC_BM, false, f16))) return rc;
   } else {
-    if ((rc = make_map(&mA, Ahi, M, K, lda, 32, TC_BK, true))) return rc;
-    if ((rc = make_map(&mAlo, Alo, M, K, lda, 32, TC_BK, true))) return rc;
+    if ((rc = make_map(&mA, Ahi, M, K, lda, mnbox, bke, true, f16))) return rc;
+    if ((rc = make_map(&mAlo, Alo, M, K, lda, mnbox, bke, true, f16))) return rc;
   }
   if (!b_mn) {
-    if ((rc = make_map(&mB, Bhi, K, N, ldb, TC_BK, BN, false))) return rc;
-    if ((rc = make_map(&mBlo, Blo, K, N, ldb, TC_BK, BN, false))) return rc;
+    if ((rc = make_map(&mB, Bhi, K, N, ldb, bke, BN, false, f16))) return rc;
+    if ((rc = make_map(&mBlo, Blo, K, N, ldb, bke, BN, false, f16))) return rc;
   } else {
-    if ((rc = make_map(&mB, Bhi, N, K, ldb, 32, TC_BK, true))) return rc;
-    if ((rc = make_map(&mBlo, Blo, N, K, ldb, 32, TC_BK, true))) return rc;
+    if ((rc = make_map(&mB, Bhi, N, K, ldb, mnbox, bke, true, f16))) return rc;
+    if ((rc = make_map(&mBlo, Blo, N, K, ldb, mnbox, bke, true, f16))) return rc;
   }
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
-  p.Chi = Chi; p.Clo = Clo;
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  p.Chi = Chi; p.Clo = Clo; p.expA = expA; p.expB = expB; p.amax = amax;
+  const int num_kb = (K + bke - 1) / bke;
   const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
   int splits = 1;
   if (act == IPAVSR_ACT_LINEAR && Chi == nullptr) {
-    if (tiles * 2 <= sm_count() && num_kb >= 32) {         // fill the machine for skinny outputs
+    if (tiles * 2 <= sm_count() && num_kb >= 32 && amax == nullptr) {         // fill the machine for skinny outputs
       splits = sm_count() / tiles;
       if (splits > num_kb / 8) splits = num_kb / 8;
     }
@@ -505,12 +567,17 @@ static int gemm_tc_core(bool x3, int transA, int transB, int M, int N, int K, co
   if (splits > 1 && !accumulate)
     IPAVSR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
 #define IPAVSR_TC_DISPATCH(BNV)                                                                       \
-  return x3 ? dispatch_major<BNV, 3>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)                           \
-            : dispatch_major<BNV, 1>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)
+  rc = f16 ? dispatch_major<BNV, 3, true>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)                      \
+           : (x3 ? dispatch_major<BNV, 3, false>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)               \
+                 : dispatch_major<BNV, 1, false>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st))
   if (BN == 64) { IPAVSR_TC_DISPATCH(64); }
-  if (BN == 128) { IPAVSR_TC_DISPATCH(128); }
-  IPAVSR_TC_DISPATCH(256);
+  else if (BN == 128) { IPAVSR_TC_DISPATCH(128); }
+  else { IPAVSR_TC_DISPATCH(256); }
 #undef IPAVSR_TC_DISPATCH
+  if (rc) return rc;
+  // split-K accumulates with atomics, so the kernel cannot produce |C|max itself: one extra pass over C
+  if (amax != nullptr && splits > 1) return amax_launch(C, ldc, M, N, amax, st);
+  return IPAVSR_OK;
 }
 
 int tf32_split_launch(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
@@ -542,15 +609,30 @@ int gemm_tc(int mode, int transA, int transB, int M, int N, int K, const float* 
     if ((rc = tf32_split_launch(B, bh, bl, b_n, st))) return rc;
     Ahi = ah; Alo = al; Bhi = bh; Blo = bl;
   }
-  return gemm_tc_core(x3, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate, nullptr,
-                      nullptr, st);
+  return gemm_tc_core(x3 ? 1 : 0, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate,
+                      nullptr, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 int gemm_tc_presplit(int transA, int transB, int M, int N, int K, const float* Ahi, const float* Alo, int lda,
                      const float* Bhi, const float* Blo, int ldb, float* C, int ldc, const float* bias, int act,
                      int accumulate, float* Chi, float* Clo, cudaStream_t st) {
-  return gemm_tc_core(true, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate, Chi,
-                      Clo, st);
+  return gemm_tc_core(1, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate, Chi,
+                      Clo, nullptr, nullptr, nullptr, st);
+}
+
+// fp16 three-product GEMM on operands split by f16split.cu (hi/lo fp16 arrays, leading dimensions in halves)
+int gemm_tc_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* Ahi, const uint16_t* Alo, int lda,
+                  const int32_t* expA, const uint16_t* Bhi, const uint16_t* Blo, int ldb, const int32_t* expB, float* C,
+                  int ldc, const float* bias, int act, int accumulate, float* amax, cudaStream_t st) {
+  return gemm_tc_core(2, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate, nullptr,
+                      nullptr, expA, expB, amax, st);
+}
+
+bool gemm_tc_f16_supported(int M, int N, int K, const void* A, int lda, const void* B, int ldb) {
+  if (!aligned16(A) || !aligned16(B) || lda % 8 != 0 || ldb % 8 != 0) return false;
+  if (K < 16 || M < 1 || N < 8) return false;
+  if ((double)M * N * K < 4.0e6) return false;
+  return true;
 }
 
 }  // namespace ipavsr
