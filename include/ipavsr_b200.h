@@ -225,6 +225,10 @@ int ipavsr_diff_image(const float* x, int ldx, float* y, int ldy, const int64_t*
 int ipavsr_deltas_fir(const float* x, int ldx, double* y, int ldy, const int64_t* offsets, int U, int F, int w,
                       int max_len, void* stream);
 
+/* profiling aid: when buf != NULL every tensor-core GEMM CTA writes 8 uint64 globaltimer stamps to
+ * buf[8 * linear_cta_id ...] = {start, setup done, first stage landed, last MMA issued, accumulator ready, epilogue done} */
+int ipavsr_debug_gemm_timestamps(unsigned long long* buf);
+
 /* ---- helpers ------------------------------------------------------------------------------------------ */
 int ipavsr_fill(float* p, uint64_t n, float v, void* stream);
 /* lo = x - tf32_trunc(x) (and optionally hi = tf32_trunc(x)) for the 3xTF32 GEMM mode */

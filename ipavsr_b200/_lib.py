@@ -61,6 +61,7 @@ _SIGS = {
     'ipavsr_seq_mean_sub': (I, [P, I, P, I, P, I, I, P]),
     'ipavsr_diff_image': (I, [P, I, P, I, P, I, I, P]),
     'ipavsr_deltas_fir': (I, [P, I, P, I, P, I, I, I, I, P]),
+    'ipavsr_debug_gemm_timestamps': (I, [P]),
     'ipavsr_fill': (I, [P, U64, F, P]),
     'ipavsr_tf32_split': (I, [P, P, P, U64, P]),
 }

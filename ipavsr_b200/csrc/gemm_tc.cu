@@ -23,6 +23,7 @@
 // [32 k-rows x 32 floats] (TMA swizzle 128B_ATOM_32B) and is consumed through MN-major UMMA descriptors
 // (SWIZZLE_128B_BASE32B) — no transposed copies are made.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ipavsr {
@@ -88,6 +89,58 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc,
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the leader CTA (cluster rank 0) issues one MMA for both SMs; each CTA's TMA
+// loads complete on the LEADER's full barrier; the leader's commit arrives on the barriers of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_cg2(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <bool F16>
+__device__ __forceinline__ void tcgen05_mma_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  if (F16)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -105,6 +158,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Epilogue nonlinearities.  sigmoid as 1 / (1 + 2^(-x log2 e)) with ex2.approx / rcp.approx (each <= 2 ulp): relative
+// error ~3e-7 + |x| * 4e-8, far inside the GEMM's own rounding; saturates correctly (ex2 -> 0 / inf, rcp(inf) = 0).
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float act_epi(float z, int act) {
+  return act == IPAVSR_ACT_SIGMOID ? sigmoid_fast(z) : act_fwd(z, act);
 }
 
 // a = hi + lo (+ ~2^-22 |a|) with hi and lo exactly representable in tf32
@@ -132,9 +213,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // instruction descriptor: D=f32, A=B=tf32 (format 2, kind::tf32) or fp16 (format 0, kind::f16), majors, N>>3, M>>4
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, bool f16) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, bool f16, int m = TC_BM) {
   return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
-         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct TcParams {
@@ -151,9 +232,19 @@ struct TcParams {
   const int32_t* expA;   // f16 mode: per-tensor scale exponents of the operands (device), result *= 2^-(eA+eB)
   const int32_t* expB;
   float* amax;           // optional (device): atomic max of |C| over the written elements (feeds the next fp16 split)
+  unsigned long long* dbg;   // optional (device): per-CTA phase timestamps (globaltimer ns), see tools/gemm_phases.py
 };
 
-template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16>
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// CG = 2: a CTA pair (cluster (2,1,1), same TPC) computes a 256 x BN tile with one cta_group::2 MMA per k-step: each CTA
+// keeps its own 128 rows of A and HALF of the B tile in shared memory (the tensor core of each SM reads both halves),
+// which cuts the L2->SM operand traffic per flop by a third and the shared-memory reads per MMA by a third.
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, TcParams p) {
@@ -161,7 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int MNBOX = F16 ? 64 : 32;                // MN-major TMA box: 128 bytes of M/N x BKE k-rows
   constexpr int MNBOX_BYTES = BKE * 128;
   constexpr int A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
-  constexpr int B_BYTES = BN * TC_BK * 4;
+  constexpr int BNL = BN / CG;                        // B-tile columns this CTA loads
+  constexpr int B_BYTES = BNL * TC_BK * 4;
+  static_assert(BNL % MNBOX == 0, "the per-CTA share of the B tile must be whole TMA boxes");
   constexpr int NOPER = (NPROD == 3) ? 2 : 1;         // hi (+ lo) copies of each operand
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
   constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
@@ -178,14 +271,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bias[256];        // bias of this tile's columns (zero where absent)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  unsigned long long* dbg = nullptr;
+  if (p.dbg != nullptr)
+    dbg = p.dbg + 8ull * (blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z));
+  if (dbg != nullptr && threadIdx.x == 0) dbg[0] = gtimer();       // CTA start
+  // pair variant: the grid is (row tiles, column tiles) so that the two CTAs of a cluster (2,1,1) are adjacent row tiles
+  const int m0 = (CG == 2 ? blockIdx.x : blockIdx.y) * TC_BM, n0 = (CG == 2 ? blockIdx.y : blockIdx.x) * BN;
+  const uint32_t crank = (CG == 2) ? cluster_ctarank() : 0u;     // 0 = leader of the pair
+  const int nl0 = n0 + (int)crank * BNL;                         // first B column this CTA loads
   const int num_kb_total = (p.K + BKE - 1) / BKE;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + p.kb_per_split);
   const int num_kb = max(kb_end - kb_begin, 0);
 
+  if (threadIdx.x < BN) {
+    const int c = (CG == 2 ? blockIdx.y : blockIdx.x) * BN + threadIdx.x;
+    s_bias[threadIdx.x] = (p.bias != nullptr && c < p.N) ? __ldg(p.bias + c) : 0.f;
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -195,15 +300,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();     // the peer's barriers must be initialised before anything can arrive on them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (dbg != nullptr && threadIdx.x == 0) dbg[1] = gtimer();       // setup done (barriers, TMEM, cluster sync)
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -213,37 +327,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
       uint8_t* sB = sA + NOPER * A_BYTES;
-      mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
       const int k0 = (kb_begin + kb) * BKE;
+      if (CG == 2) {
+        // both CTAs' loads complete on the leader's barrier, which therefore expects the bytes of both
+        if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+        const uint32_t fb = mapa_shared(smem_u32(&full_bar[stage]), 0);
 #pragma unroll
-      for (int o = 0; o < NOPER; ++o) {
-        const CUtensorMap* ma = o == 0 ? &mapA : &mapAlo;
-        const CUtensorMap* mb = o == 0 ? &mapB : &mapBlo;
-        if (!A_MN) {
-          tma_load_2d(sA + o * A_BYTES, ma, &full_bar[stage], k0, m0);                 // box {32 k, 128 rows}
-        } else {
+        for (int o = 0; o < NOPER; ++o) {
+          const CUtensorMap* ma = o == 0 ? &mapA : &mapAlo;
+          const CUtensorMap* mb = o == 0 ? &mapB : &mapBlo;
+          if (!A_MN) {
+            tma_load_2d_cg2(sA + o * A_BYTES, ma, fb, k0, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < TC_BM / MNBOX; ++j)                                      // boxes {128 B of m, BKE k-rows}
-            tma_load_2d(sA + o * A_BYTES + j * MNBOX_BYTES, ma, &full_bar[stage], m0 + MNBOX * j, k0);
+            for (int j = 0; j < TC_BM / MNBOX; ++j)
+              tma_load_2d_cg2(sA + o * A_BYTES + j * MNBOX_BYTES, ma, fb, m0 + MNBOX * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d_cg2(sB + o * B_BYTES, mb, fb, k0, nl0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BNL / MNBOX; ++j)
+              tma_load_2d_cg2(sB + o * B_BYTES + j * MNBOX_BYTES, mb, fb, nl0 + MNBOX * j, k0);
+          }
         }
-        if (!B_MN) {
-          tma_load_2d(sB + o * B_BYTES, mb, &full_bar[stage], k0, n0);
-        } else {
+      } else {
+        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
 #pragma unroll
-          for (int j = 0; j < BN / MNBOX; ++j)
-            tma_load_2d(sB + o * B_BYTES + j * MNBOX_BYTES, mb, &full_bar[stage], n0 + MNBOX * j, k0);
+        for (int o = 0; o < NOPER; ++o) {
+          const CUtensorMap* ma = o == 0 ? &mapA : &mapAlo;
+          const CUtensorMap* mb = o == 0 ? &mapB : &mapBlo;
+          if (!A_MN) {
+            tma_load_2d(sA + o * A_BYTES, ma, &full_bar[stage], k0, m0);                 // box {32 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < TC_BM / MNBOX; ++j)                                      // boxes {128 B of m, BKE k-rows}
+              tma_load_2d(sA + o * A_BYTES + j * MNBOX_BYTES, ma, &full_bar[stage], m0 + MNBOX * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB + o * B_BYTES, mb, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / MNBOX; ++j)
+              tma_load_2d(sB + o * B_BYTES + j * MNBOX_BYTES, mb, &full_bar[stage], n0 + MNBOX * j, k0);
+          }
         }
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN, F16);
+  } else if (warp == 1 && lane == 0 && crank == 0) {
+    // ===================== MMA issuer (leader CTA only in the pair variant) =====================
+    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN, F16, TC_BM * CG);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tcgen05_fence_after();
+      if (dbg != nullptr && kb == 0) dbg[2] = gtimer();            // first stage landed
       const uint32_t sA = smem_u32(smem + (size_t)stage * STAGE_BYTES);
       const uint32_t sB = sA + NOPER * A_BYTES;
 #pragma unroll
@@ -268,7 +408,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t t_cross = tmem_base + (uint32_t)(NMAIN * BN);
           const uint32_t t_main = tmem_base + (uint32_t)((kb % NMAIN) * BN);
           const uint32_t main_acc = (kb < NMAIN && k == 0) ? 0u : 1u;
-          if (F16) {
+          if (CG == 2) {
+            tcgen05_mma_cg2<F16>(t_cross, a_lo, b_hi, idesc, first);
+            tcgen05_mma_cg2<F16>(t_cross, a_hi, b_lo, idesc, 1u);
+            tcgen05_mma_cg2<F16>(t_main, a_hi, b_hi, idesc, main_acc);
+          } else if (F16) {
             tcgen05_mma_f16(t_cross, a_lo, b_hi, idesc, first);
             tcgen05_mma_f16(t_cross, a_hi, b_lo, idesc, 1u);
             tcgen05_mma_f16(t_main, a_hi, b_hi, idesc, main_acc);
@@ -278,37 +422,141 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tcgen05_mma_tf32(t_main, a_hi, b_hi, idesc, main_acc);
           }
         } else {
-          tcgen05_mma_tf32(tmem_base, a_hi, b_hi, idesc, first);
+          if (CG == 2) tcgen05_mma_cg2<false>(tmem_base, a_hi, b_hi, idesc, first);
+          else tcgen05_mma_tf32(tmem_base, a_hi, b_hi, idesc, first);
         }
       }
-      tcgen05_commit(&empty_bar[stage]);          // frees this shared stage once the MMAs above have read it
+      // frees this shared stage (in both CTAs of a pair) once the MMAs above have read it
+      if (CG == 2) tcgen05_commit_cg2(&empty_bar[stage]);
+      else tcgen05_commit(&empty_bar[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-    tcgen05_commit(&accum_bar);                   // accumulator complete
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // accumulator complete
+    if (CG == 2) tcgen05_commit_cg2(&accum_bar);
+    else tcgen05_commit(&accum_bar);
+    if (dbg != nullptr) dbg[3] = gtimer();                         // last MMA issued
+  }
+  __syncwarp();
+  {
+    // ===================== epilogue: all 8 warps =====================
+    // Warp w reads TMEM lanes 32*(w%4).. (one output row per thread); warps 4-7 take the even 32-column chunks and
+    // warps 0-3 (whose producer / MMA-issuer lanes have finished by now) the odd ones, so every SM sub-partition has
+    // two warps to hide the epilogue's latencies behind each other.
     const int q = warp & 3;                        // TMEM lane quadrant of this warp
     const int row = m0 + q * 32 + lane;
     if (num_kb > 0) {
       mbar_wait(&accum_bar, 0);
       tcgen05_fence_after();
     }
+    if (dbg != nullptr && threadIdx.x == 128) dbg[4] = gtimer();   // accumulator complete: epilogue starts
     const bool split = p.splits > 1;
     const bool vec = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
-    float osc1 = 1.f, osc2 = 1.f;                  // f16 mode: result = acc * 2^-(eA+eB), applied as two exact factors
+    // f16 mode: result = (main + cross * 2^-11) * 2^-(eA+eB); one exact factor when it is a normal float, else two
+    float ms1 = 1.f, ms2 = 1.f;
     if (F16) {
       const int e = -(__ldg(p.expA) + __ldg(p.expB));
-      const int e1 = e / 2, e2 = e - e1;
-      osc1 = __int_as_float((127 + e1) << 23);
-      osc2 = __int_as_float((127 + e2) << 23);
+      const int e1 = (e > 126 || e < -115) ? e / 2 : e, e2 = e - e1;
+      ms1 = __int_as_float((127 + e1) << 23);
+      ms2 = __int_as_float((127 + e2) << 23);
     }
+    const float cs1 = F16 ? ms1 * (1.0f / 2048.0f) : 1.f;
     float tile_max = 0.f;
+    const bool fast_ok = vec && !split && num_kb > 0;      // warp-uniform
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = (warp >= 4 ? 0 : 32); c0 < BN; c0 += 64) {
       if (n0 + c0 >= p.N) break;                   // warp-uniform
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      if (fast_ok && n0 + c0 + 32 <= p.N) {
+        // ---------------- fast path: a full 32-column chunk, vector stores, compile-time activation ----------------
+        float v[32];
+        if (NPROD == 3) {
+          float u[32];
+          tmem_ld32_issue(lane_base + (uint32_t)(NMAIN * BN), v);           // cross terms
+          tmem_ld32_issue(lane_base, u);                                    // first main accumulator
+          tmem_ld_wait();
+          if (F16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], cs1, u[j] * ms1);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
+          const int used = num_kb < NMAIN ? num_kb : NMAIN;
+#pragma unroll 1
+          for (int a = 1; a < used; ++a) {
+            tmem_ld32_issue(lane_base + (uint32_t)(a * BN), u);
+            tmem_ld_wait();
+            if (F16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaf(u[j], ms1, v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
+          }
+          if (F16 && ms2 != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ms2;
+          }
+        } else {
+          tmem_ld32_issue(lane_base, v);
+          tmem_ld_wait();
+        }
+        if (row < p.M) {
+          float* cp = p.C + (size_t)row * p.ldc + n0 + c0;
+          if (p.accumulate) {
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              const float4 old = *reinterpret_cast<const float4*>(cp + j4);
+              v[j4] += old.x; v[j4 + 1] += old.y; v[j4 + 2] += old.z; v[j4 + 3] += old.w;
+            }
+          }
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + j4]);
+              v[j4] += b4.x; v[j4 + 1] += b4.y; v[j4 + 2] += b4.z; v[j4 + 3] += b4.w;
+            }
+          }
+          switch (p.act) {
+            case IPAVSR_ACT_LINEAR: break;
+            case IPAVSR_ACT_SIGMOID:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
+              break;
+            case IPAVSR_ACT_RECTIFY:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              break;
+            default:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
+              break;
+          }
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4)
+            *reinterpret_cast<float4*>(cp + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+          if (p.amax != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tile_max = fmaxf(tile_max, fabsf(v[j]));
+          }
+          if (p.Chi != nullptr) {
+            const size_t off = (size_t)row * p.ldc + n0 + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              float4 h, l;
+              tf32_hi_lo(v[j4], h.x, l.x); tf32_hi_lo(v[j4 + 1], h.y, l.y);
+              tf32_hi_lo(v[j4 + 2], h.z, l.z); tf32_hi_lo(v[j4 + 3], h.w, l.w);
+              *reinterpret_cast<float4*>(p.Chi + off + j4) = h;
+              *reinterpret_cast<float4*>(p.Clo + off + j4) = l;
+            }
+          }
+        }
+        continue;
+      }
+      // ---------------- general path: ragged edges, split-K atomics, unaligned C ----------------
       float v[32];
       if (num_kb > 0) {
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         if (NPROD == 3) {
           tmem_ld32(lane_base + (uint32_t)(NMAIN * BN), v);                 // cross terms first (smallest)
           if (F16) {
@@ -325,7 +573,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           if (F16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * osc1 * osc2;
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * ms1 * ms2;
           }
         } else {
           tmem_ld32(lane_base, v);
@@ -337,13 +585,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (row < p.M) {
         float* cp = p.C + (size_t)row * p.ldc + n0 + c0;
         if (split) {
+          if (vec && n0 + c0 + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < p.N) {
-              float add = v[j];
-              if (p.bias != nullptr && blockIdx.z == 0) add += __ldg(p.bias + n0 + c0 + j);
-              atomicAdd(cp + j, add);
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              float4 add = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+              if (p.bias != nullptr && blockIdx.z == 0) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + j4]);
+                add.x += b4.x; add.y += b4.y; add.z += b4.z; add.w += b4.w;
+              }
+              atomicAdd(reinterpret_cast<float4*>(cp + j4), add);
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < p.N) {
+                float add = v[j];
+                if (p.bias != nullptr && blockIdx.z == 0) add += s_bias[c0 + j];
+                atomicAdd(cp + j, add);
+              }
+          }
         } else {
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -356,10 +616,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
               }
               if (p.bias != nullptr) {
-                o.x += __ldg(p.bias + col); o.y += __ldg(p.bias + col + 1);
-                o.z += __ldg(p.bias + col + 2); o.w += __ldg(p.bias + col + 3);
+                o.x += s_bias[c0 + j4]; o.y += s_bias[c0 + j4 + 1];
+                o.z += s_bias[c0 + j4 + 2]; o.w += s_bias[c0 + j4 + 3];
               }
-              o.x = act_fwd(o.x, p.act); o.y = act_fwd(o.y, p.act); o.z = act_fwd(o.z, p.act); o.w = act_fwd(o.w, p.act);
+              o.x = act_epi(o.x, p.act); o.y = act_epi(o.y, p.act); o.z = act_epi(o.z, p.act); o.w = act_epi(o.w, p.act);
               *reinterpret_cast<float4*>(cp + j4) = o;
               tile_max = fmaxf(tile_max, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
               if (p.Chi != nullptr) {
@@ -375,8 +635,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (col + j < p.N) {
                   float o = v[j4 + j];
                   if (p.accumulate) o += cp[j4 + j];
-                  if (p.bias != nullptr) o += __ldg(p.bias + col + j);
-                  o = act_fwd(o, p.act);
+                  if (p.bias != nullptr) o += s_bias[c0 + j4 + j];
+                  o = act_epi(o, p.act);
                   cp[j4 + j] = o;
                   tile_max = fmaxf(tile_max, fabsf(o));
                   if (p.Chi != nullptr) {
@@ -396,12 +656,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (lane == 0 && tile_max > 0.f) atomicMax(reinterpret_cast<unsigned int*>(p.amax), __float_as_uint(tile_max));
     }
     tcgen05_fence_before();
+    if (dbg != nullptr && threadIdx.x == 128) dbg[5] = gtimer();   // epilogue done (even chunks)
+    if (dbg != nullptr && threadIdx.x == 0) dbg[6] = gtimer();     // epilogue done (odd chunks)
   }
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();     // the leader's MMAs read the peer's shared memory and write its TMEM
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -463,6 +730,8 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   return IPAVSR_OK;
 }
 
+unsigned long long* g_gemm_dbg = nullptr;      // set by ipavsr_debug_gemm_timestamps (profiling aid)
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -487,29 +756,47 @@ uint64_t gemm_tc_workspace_bytes(int mode, int transA, int transB, int M, int N,
   return 2 * (a + b) * sizeof(float) * 2;   // x2 head-room for leading dimensions up to twice the logical width
 }
 
-template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16>
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo,
                      TcParams p, cudaStream_t st) {
-  constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
+  constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = (BN / CG) * TC_BK * 4;
   constexpr int NOPER = (NPROD == 3) ? 2 : 1;
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
   constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD, F16>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD, F16, CG>;
   IPAVSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((p.N + BN - 1) / BN, (p.M + TC_BM - 1) / TC_BM, p.splits);
-  kern<<<grid, TC_THREADS, smem, st>>>(mA, mAlo, mB, mBlo, p);
+  const int mtiles = (p.M + TC_BM - 1) / TC_BM;
+  dim3 grid((p.N + BN - 1) / BN, mtiles, p.splits);
+  if (CG == 2) grid = dim3((mtiles + 1) / 2 * 2, (p.N + BN - 1) / BN, p.splits);
+  if (CG == 1) {
+    kern<<<grid, TC_THREADS, smem, st>>>(mA, mAlo, mB, mBlo, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    IPAVSR_CUDA(cudaLaunchKernelEx(&cfg, kern, mA, mAlo, mB, mBlo, p));
+  }
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }
 
-template <int BN, int NPROD, bool F16>
+template <int BN, int NPROD, bool F16, int CG>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
                           const CUtensorMap& mBlo, TcParams p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
-  return launch_tc<BN, true, true, NPROD, F16>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
+  return launch_tc<BN, true, true, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
 }
 
 int amax_launch(const float* x, int ldx, int rows, int cols, float* amax, cudaStream_t st);   // f16split.cu
@@ -536,9 +823,16 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
     if ((rc = make_map(&mA, Ahi, M, K, lda, mnbox, bke, true, f16))) return rc;
     if ((rc = make_map(&mAlo, Alo, M, K, lda, mnbox, bke, true, f16))) return rc;
   }
+  // CTA pairs (cta_group::2) for wide outputs with at least two row tiles; IPAVSR_GEMM_CG=1 forces single-CTA tiles
+  static int cg_env = -1;
+  if (cg_env < 0) {
+    const char* e = getenv("IPAVSR_GEMM_CG");
+    cg_env = (e && e[0] == '1') ? 1 : 2;
+  }
+  const int cg = (BN == 256 && M > TC_BM && cg_env == 2) ? 2 : 1;
   if (!b_mn) {
-    if ((rc = make_map(&mB, Bhi, K, N, ldb, bke, BN, false, f16))) return rc;
-    if ((rc = make_map(&mBlo, Blo, K, N, ldb, bke, BN, false, f16))) return rc;
+    if ((rc = make_map(&mB, Bhi, K, N, ldb, bke, BN / cg, false, f16))) return rc;
+    if ((rc = make_map(&mBlo, Blo, K, N, ldb, bke, BN / cg, false, f16))) return rc;
   } else {
     if ((rc = make_map(&mB, Bhi, N, K, ldb, mnbox, bke, true, f16))) return rc;
     if ((rc = make_map(&mBlo, Blo, N, K, ldb, mnbox, bke, true, f16))) return rc;
@@ -546,8 +840,9 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
   p.Chi = Chi; p.Clo = Clo; p.expA = expA; p.expB = expB; p.amax = amax;
+  p.dbg = g_gemm_dbg;
   const int num_kb = (K + bke - 1) / bke;
-  const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+  const int tiles = ((M + TC_BM * cg - 1) / (TC_BM * cg)) * cg * ((N + BN - 1) / BN);
   int splits = 1;
   if (act == IPAVSR_ACT_LINEAR && Chi == nullptr) {
     if (tiles * 2 <= sm_count() && num_kb >= 32 && amax == nullptr) {         // fill the machine for skinny outputs
@@ -566,13 +861,14 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
   p.splits = splits;
   if (splits > 1 && !accumulate)
     IPAVSR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
-#define IPAVSR_TC_DISPATCH(BNV)                                                                       \
-  rc = f16 ? dispatch_major<BNV, 3, true>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)                      \
-           : (x3 ? dispatch_major<BNV, 3, false>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)               \
-                 : dispatch_major<BNV, 1, false>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st))
-  if (BN == 64) { IPAVSR_TC_DISPATCH(64); }
-  else if (BN == 128) { IPAVSR_TC_DISPATCH(128); }
-  else { IPAVSR_TC_DISPATCH(256); }
+#define IPAVSR_TC_DISPATCH(BNV, CGV)                                                                  \
+  rc = f16 ? dispatch_major<BNV, 3, true, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)                 \
+           : (x3 ? dispatch_major<BNV, 3, false, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)          \
+                 : dispatch_major<BNV, 1, false, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st))
+  if (BN == 64) { IPAVSR_TC_DISPATCH(64, 1); }
+  else if (BN == 128) { IPAVSR_TC_DISPATCH(128, 1); }
+  else if (cg == 2) { IPAVSR_TC_DISPATCH(256, 2); }
+  else { IPAVSR_TC_DISPATCH(256, 1); }
 #undef IPAVSR_TC_DISPATCH
   if (rc) return rc;
   // split-K accumulates with atomics, so the kernel cannot produce |C|max itself: one extra pass over C
@@ -636,3 +932,8 @@ bool gemm_tc_f16_supported(int M, int N, int K, const void* A, int lda, const vo
 }
 
 }  // namespace ipavsr
+
+extern "C" int ipavsr_debug_gemm_timestamps(unsigned long long* buf) {
+  ipavsr::g_gemm_dbg = buf;
+  return IPAVSR_OK;
+}
