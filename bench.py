@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the AdeNet hot path on B200 (contract: see DESIGN.md "Measurement").
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B] [--mode fp32|tf32x3|tf32]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B] [--mode f16x3|tf32x3|fp32|tf32]
 
 Workload (config.workload): the AdeNet-v2 late-fusion *trimodal* network (`modelzoo.adenet_3stream`:
 raw 1200-px ROI + diff-image 1200-px + DCT 90, each through a DBNF encoder 2000-1000-500-50 -> DeltaLayer(theta=9) ->
@@ -157,8 +157,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--batch', type=int, default=512, help='utterances per GPU per step')
-    ap.add_argument('--mode', default=os.environ.get('IPAVSR_GEMM_MODE', 'tf32x3'),
-                    help='GEMM arithmetic: tf32x3 (fp32-parity, default) | fp32 (CUDA cores) | tf32 (single pass)')
+    ap.add_argument('--mode', default=os.environ.get('IPAVSR_GEMM_MODE', 'f16x3'),
+                    help='GEMM arithmetic: f16x3 (fp32-parity 3-product fp16 tensor cores, default) | tf32x3 (fp32-parity '
+                         '3xTF32) | fp32 (CUDA cores) | tf32 (single pass)')
     ap.add_argument('--cpu-sample', type=int, default=26)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
@@ -268,7 +269,7 @@ def main():
         B = torch.randn(K, N, device='cuda')
         Cm = torch.empty(M, N, device='cuda')
         bias = torch.zeros(N, device='cuda')
-        mode = {'fp32': 0, 'tf32x3': 1, 'tf32': 2}[args.mode]
+        mode = {'fp32': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 4}[args.mode]
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         flush = torch.empty(192 * 1024 * 1024 // 4, device='cuda')
         if mode == 1:
@@ -279,6 +280,18 @@ def main():
             _lib.call('ipavsr_tf32_split_rna', B.data_ptr(), bh.data_ptr(), bl.data_ptr(), B.numel(), st)
             run = lambda: _lib.call('ipavsr_gemm_tf32x3_presplit', 0, 0, M, N, K, ah.data_ptr(), al.data_ptr(), K,
                                     bh.data_ptr(), bl.data_ptr(), N, Cm.data_ptr(), N, bias.data_ptr(), 1, 0, None, None, st)
+        elif mode == 4:
+            # likewise for the fp16 three-product mode: operands arrive as fp16 hi/lo + per-tensor scale exponents
+            ah, al = torch.empty(M, K, dtype=torch.float16, device='cuda'), torch.empty(M, K, dtype=torch.float16, device='cuda')
+            bh, bl = torch.empty(K, N, dtype=torch.float16, device='cuda'), torch.empty(K, N, dtype=torch.float16, device='cuda')
+            sc = torch.zeros(4, device='cuda')
+            _lib.call('ipavsr_f16_split', A.data_ptr(), K, M, K, ah.data_ptr(), al.data_ptr(), K, sc.data_ptr(),
+                      sc.data_ptr() + 4, 0, st)
+            _lib.call('ipavsr_f16_split', B.data_ptr(), N, K, N, bh.data_ptr(), bl.data_ptr(), N, sc.data_ptr() + 8,
+                      sc.data_ptr() + 12, 0, st)
+            run = lambda: _lib.call('ipavsr_gemm_f16x3', 0, 0, M, N, K, ah.data_ptr(), al.data_ptr(), K, sc.data_ptr() + 4,
+                                    bh.data_ptr(), bl.data_ptr(), N, sc.data_ptr() + 12, Cm.data_ptr(), N, bias.data_ptr(),
+                                    1, 0, None, st)
         else:
             run = lambda: _lib.call('ipavsr_gemm', mode, 0, 0, M, N, K, A.data_ptr(), K, B.data_ptr(), N, Cm.data_ptr(), N,
                                     bias.data_ptr(), 1, 0, None, 0, st)
@@ -312,8 +325,11 @@ def main():
         roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel: encoder fc1 GEMM %dx%dx%d (%s)' % (M, N, K, args.mode),
                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                     'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback 1.59 PFLOP/s',
-                    'note': 'algorithmic FLOPs; fp32 parity on tf32 tensor cores costs 3 MMAs/product and tf32 peak is '
-                            'half of bf16, so the ceiling of this mode is 1/6 of the bf16 peak',
+                    'note': {'f16x3': 'algorithmic FLOPs; fp32 parity on 16-bit tensor cores costs 3 MMAs per product, so the '
+                                      'ceiling of this mode is 1/3 of the bf16 peak',
+                             'tf32x3': 'algorithmic FLOPs; fp32 parity on tf32 tensor cores costs 3 MMAs/product and tf32 peak '
+                                       'is half of bf16, so the ceiling of this mode is 1/6 of the bf16 peak'}.get(
+                                 args.mode, 'algorithmic FLOPs'),
                     'ms_per_launch': gemm_ms}
         if not args.no_cpu_baseline and world == 1:
             rate, spstep = cpu_reference_step_rate(args.cpu_sample, 2, 1)

@@ -26,14 +26,16 @@ from . import layers as L
 
 ACT = {'linear': 0, 'sigmoid': 1, 'rectify': 2, 'tanh': 3, 'leaky_rectify': 4, 'very_leaky_rectify': 5,
        'softplus': 6, 'elu': 7}
-GEMM_MODES = {'fp32': 0, 'tf32x3': 1, 'tf32': 2}
+GEMM_MODES = {'fp32': 0, 'tf32x3': 1, 'tf32': 2, 'f16x3': 4}
 OPT = {'adam': 0, 'adadelta': 1, 'sgd': 2, 'momentum': 3, 'nesterov': 4}
 GATES = ('ingate', 'forgetgate', 'cell', 'outgate')
 SEG = 256    # arena alignment in floats
 
 
-def _ld4(c):
-    return (int(c) + 3) // 4 * 4
+def _ld8(c):
+    """Leading dimension of a device matrix: a multiple of 8 floats, so that both the float32 rows (vector loads, TMA)
+    and the fp16 hi/lo copies of the same shape (16-byte TMA strides) are aligned."""
+    return (int(c) + 7) // 8 * 8
 
 
 class DevMat(object):
@@ -66,7 +68,7 @@ class ParamArena(object):
 
         def add(key, rows, cols, pad_ld=True):
             nonlocal off
-            ld = _ld4(cols) if (pad_ld and rows > 1) else cols
+            ld = _ld8(cols) if (pad_ld and rows > 1) else cols
             self.tensors[key] = (off, rows, cols, ld)
             self.order.append(key)
             off += (rows * ld + SEG - 1) // SEG * SEG
@@ -123,6 +125,13 @@ class ParamArena(object):
         self.aux = torch.zeros(max(aux, 4), dtype=torch.float32, device=device)
         self.state = {}
         self.flat_hi = self.flat_lo = None      # tf32 split of the parameters (3xTF32 mode), refreshed when dirty
+        self.flat_h16 = self.flat_l16 = None    # fp16 hi/lo split (f16x3 mode) + per-tensor scale exponents
+        self.exps = self.amaxs = self.seg_id = None
+        seg = np.zeros(max(off // SEG, 1), dtype=np.int32)
+        for i, k in enumerate(self.order):
+            o, rows, cols, ld = self.tensors[k]
+            seg[o // SEG: o // SEG + (rows * ld + SEG - 1) // SEG] = i
+        self.seg_host = seg
         self.split_dirty = True
         # upload host masters, then bind
         params = list(self.bind.keys())
@@ -245,6 +254,7 @@ class Engine(object):
         self.step_t = np.float32(0)  # Adam's shared step counter (custom/updates.py:74)
         self._ws = None
         self._split_cache = {}
+        self._amax = {}
         self._lr_cache = None
         # independent LSTM recurrences (the per-stream LSTMs; the forward/backward aggregate pair) run concurrently
         # on side streams and overlap with the GEMMs of the other branches on the main stream
@@ -260,7 +270,7 @@ class Engine(object):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def new(self, rows, cols, zero=False):
-        ld = _ld4(cols)
+        ld = _ld8(cols)
         n = max(rows * ld, 4)
         t = (torch.zeros if zero else torch.empty)(n, dtype=torch.float32, device=self.device)
         return DevMat(t, t.data_ptr(), rows, cols, ld)
@@ -299,6 +309,18 @@ class Engine(object):
     # ---- 3xTF32 operand splits: each tensor is split once per step and reused by every GEMM that reads it ----
     def _refresh_param_split(self):
         ar = self.arena
+        if self.gemm_mode == 4:
+            if ar.flat_h16 is None:
+                ar.flat_h16 = torch.empty(ar.flat.numel(), dtype=torch.float16, device=self.device)
+                ar.flat_l16 = torch.empty(ar.flat.numel(), dtype=torch.float16, device=self.device)
+                ar.seg_id = torch.from_numpy(ar.seg_host).to(self.device)
+                ar.exps = torch.zeros(len(ar.order) + 1, dtype=torch.int32, device=self.device)
+                ar.amaxs = torch.zeros(len(ar.order) + 1, dtype=torch.float32, device=self.device)
+            if ar.split_dirty and ar.n > 0:
+                _lib.call('ipavsr_f16_split_segments', ar.flat.data_ptr(), ar.flat_h16.data_ptr(), ar.flat_l16.data_ptr(),
+                          ar.n, ar.seg_id.data_ptr(), len(ar.order), ar.amaxs.data_ptr(), ar.exps.data_ptr(), self.stream)
+                ar.split_dirty = False
+            return
         if ar.flat_hi is None:
             ar.flat_hi = torch.empty_like(ar.flat)
             ar.flat_lo = torch.empty_like(ar.flat)
@@ -325,8 +347,46 @@ class Engine(object):
             self._split_cache[key] = hit
         return hit[0], hit[1]
 
+    def _split16(self, m):
+        """fp16x3 operand of a float32 DevMat: (hi ptr, lo ptr, exponent ptr); leading dimension = m.ld halves."""
+        ar = self.arena
+        if m.t is ar.flat:
+            off = (m.ptr - ar.flat.data_ptr()) // 4
+            return (ar.flat_h16.data_ptr() + 2 * off, ar.flat_l16.data_ptr() + 2 * off,
+                    ar.exps.data_ptr() + 4 * int(ar.seg_host[off // SEG]))
+        key = (m.ptr, m.rows, m.cols, m.ld)
+        hit = self._split_cache.get(key)
+        if hit is None:
+            n = max(m.rows * m.ld, 8)
+            hi = torch.empty(n, dtype=torch.float16, device=self.device)
+            lo = torch.empty(n, dtype=torch.float16, device=self.device)
+            amax = self._amax.pop(key, None)
+            ready = amax is not None
+            if amax is None:
+                amax = torch.empty(2, dtype=torch.float32, device=self.device)
+            _lib.call('ipavsr_f16_split', m.ptr, m.ld, m.rows, m.cols, hi.data_ptr(), lo.data_ptr(), m.ld,
+                      amax.data_ptr(), amax.data_ptr() + 4, 1 if ready else 0, self.stream)
+            hit = (hi, lo, amax, m.t)
+            self._split_cache[key] = hit
+        return hit[0].data_ptr(), hit[1].data_ptr(), hit[2].data_ptr() + 4
+
     def gemm(self, A, B, Cm, M, N, K, transA=0, transB=0, bias=None, act=0, accumulate=0, emit_split=False):
         mode = self.gemm_mode
+        if mode == 4:
+            if not self.lib.ipavsr_gemm_f16_supported(M, N, K, 16, A.ld, 16, B.ld):
+                mode = 0        # tiny / unaligned products: the exact FP32 kernel
+            else:
+                ah, al, ea = self._split16(A)
+                bh, bl, eb = self._split16(B)
+                amax = None
+                if emit_split and not accumulate:
+                    # the epilogue leaves max|C| behind, so the split of C (first use as an operand) needs no reduction pass
+                    t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                    self._amax[(Cm.ptr, Cm.rows, Cm.cols, Cm.ld)] = t
+                    amax = t.data_ptr()
+                _lib.call('ipavsr_gemm_f16x3', transA, transB, M, N, K, ah, al, A.ld, ea, bh, bl, B.ld, eb,
+                          Cm.ptr, Cm.ld, bias, act, accumulate, amax, self.stream)
+                return
         if mode != 0 and not self.lib.ipavsr_gemm_tc_supported(transA, transB, M, N, K, A.ptr, A.ld, B.ptr, B.ld,
                                                                 Cm.ptr, Cm.ld):
             mode = 0        # tiny / unaligned products: the exact FP32 kernel
@@ -378,7 +438,7 @@ class Engine(object):
             return t.to(torch.int32).to(self.device, non_blocking=True).contiguous()
         t = t.to(torch.float32)
         N, T, F = t.shape
-        ld = _ld4(F)
+        ld = _ld8(F)
         if ld == F:
             d = t.to(self.device, non_blocking=True).contiguous()
             return DevMat(d, d.data_ptr(), N * T, F, F)
@@ -400,7 +460,8 @@ class Engine(object):
         N, T = int(first.shape[0]), int(first.shape[1])
         run = _Run(N, T)
         self._split_cache = {}
-        if self.gemm_mode == 1:
+        self._amax = {}
+        if self.gemm_mode in (1, 4):
             self._refresh_param_split()
         run.window = int(window) if window is not None else 0
         run.deterministic = deterministic
@@ -491,12 +552,12 @@ class Engine(object):
                     mask = torch.ones(N, T, dtype=torch.uint8, device=self.device)
                 xw = self.new(N * T, 4 * H)
                 self._proj(segs, ar.mat((l, 'W_in')), xw, ar.mat((l, 'b')).ptr, 0)
-                out = self.new(N * T, H, zero=(_ld4(H) != H))
+                out = self.new(N * T, H, zero=(_ld8(H) != H))
                 gates = cell = hprev = None
                 if train:
                     gates = self.new(N * T, 4 * H)
                     cell = self.new(N * T, H)
-                    hprev = self.new(N * T, H, zero=(_ld4(H) != H))
+                    hprev = self.new(N * T, H, zero=(_ld8(H) != H))
                     if cell.ld != H:       # cell is dense (ld = H) inside the kernels
                         cell = DevMat(cell.t, cell.ptr, N * T, H, H)
                 peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
@@ -523,7 +584,7 @@ class Engine(object):
             elif isinstance(l, (L.ElemwiseSumLayer, L.AdaptiveElemwiseSumLayer)):
                 ins = [self._single(run.vals[i]) for i in l.input_layers]
                 rows, F = ins[0].rows, ins[0].cols
-                out = self.new(rows, F, zero=(_ld4(F) != F))
+                out = self.new(rows, F, zero=(_ld8(F) != F))
                 ptrs = (C.c_void_p * len(ins))(*[i.ptr for i in ins])
                 lds = (C.c_int * len(ins))(*[i.ld for i in ins])
                 coeffs = ar.mat((l, 'coeffs')).ptr if isinstance(l, L.AdaptiveElemwiseSumLayer) else None
@@ -536,7 +597,7 @@ class Engine(object):
                 run.vals[l] = segs
             elif isinstance(l, L.SliceLayer):
                 x = self._single(run.vals[l.input_layer])
-                out = self.new(N, x.cols, zero=(_ld4(x.cols) != x.cols))
+                out = self.new(N, x.cols, zero=(_ld8(x.cols) != x.cols))
                 _lib.call('ipavsr_slice_last', x.ptr, x.ld, out.ptr, out.ld, N, T, x.cols, 0, 0, st)
                 run.vals[l] = [out]
             else:
@@ -568,13 +629,13 @@ class Engine(object):
         if layer in run.grads:
             segs, owned = run.grads[layer]
             if not owned:
-                new = [self.new(s.rows, s.cols, zero=(_ld4(s.cols) != s.cols)) for s in segs]
+                new = [self.new(s.rows, s.cols, zero=(_ld8(s.cols) != s.cols)) for s in segs]
                 for a, b in zip(segs, new):
                     _lib.call('ipavsr_copy2d', a.ptr, a.ld, b.ptr, b.ld, a.rows, a.cols, None, 0, self.stream)
                 run.grads[layer] = (new, True)
                 segs = new
             return segs, 1
-        segs = [self.new(s.rows, s.cols, zero=(_ld4(s.cols) != s.cols)) for s in like]
+        segs = [self.new(s.rows, s.cols, zero=(_ld8(s.cols) != s.cols)) for s in like]
         run.grads[layer] = (segs, True)
         return segs, 0
 
@@ -661,7 +722,7 @@ class Engine(object):
                 if self.requires_grad.get(l.input_layer, False):
                     g = gsegs[0]
                     F = g.cols // 3
-                    tgt, acc = self._grad_target(run, l.input_layer, [DevMat(None, 0, g.rows, F, _ld4(F))])
+                    tgt, acc = self._grad_target(run, l.input_layer, [DevMat(None, 0, g.rows, F, _ld8(F))])
                     _lib.call('ipavsr_delta_bwd', g.ptr, g.ld, tgt[0].ptr, tgt[0].ld, N, T, F, run.window, acc, st)
             elif isinstance(l, L.LSTMLayer):
                 H = l.num_units
@@ -836,6 +897,7 @@ class Engine(object):
         ar, st = self.arena, self.stream
         ar.split_dirty = True
         self._split_cache = {}
+        self._amax = {}
         n = ar.n
         seg_lr = seg_id = None
         if lr_map is not None:

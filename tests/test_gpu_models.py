@@ -64,6 +64,47 @@ def test_forward_backward_parity(name):
             assert err < 2e-3, (name, fusiontype, p.name, err, scale)
 
 
+@pytest.mark.parametrize('mode', ['f16x3', 'tf32x3'])
+def test_tensor_core_modes_at_reference_sizes(mode):
+    """The fp32-parity tensor-core GEMM modes on the real layer sizes (D=1200, DBNF 2000-1000-500-50, DCT 90, LSTM-250,
+    26 classes, T=40): same gates as the CUDA-core fp32 mode — probabilities 1e-4, identical argmax, gradients 2e-3."""
+    from ipavsr_b200 import modelzoo, init
+    rng = np.random.default_rng(77)
+    np.random.seed(77)
+    D, Dd, H, C, win, N, T_ = 1200, 90, 250, 26, 9, 24, 40
+    ae = MU.ae_tuple(rng, D, shapes=(2000, 1000, 500, 50), acts=('sigmoid', 'sigmoid', 'sigmoid', 'linear'))
+    net, _ = modelzoo.adenet_v2.create_model(ae, (None, None, D), T.tensor3('x'), (None, None),
+                                             T.matrix('mask', dtype='uint8'), (None, None, Dd), T.tensor3('dct'), H, win, C,
+                                             'concat', init.Orthogonal(), True)
+    MU.randomize_params(net, rng)
+    lens = rng.integers(12, T_ + 1, size=N)
+    lens[0] = T_
+    xs, mask, _ = MU.make_feed(rng, N, T_, [D, Dd], lens=lens)
+    y = np.repeat(rng.integers(0, C, size=(N, 1)), T_, 1).astype('int32')
+    feed = {'input': xs[0], 'dct': xs[1], 'mask': mask}
+    loss_ref, out_ref, grads_ref = OracleNet(net, np.float64).loss_and_grads(feed, win, y, mask, 'temporal_softmax',
+                                                                            deterministic=False, update_bn=False)
+    eng = Engine(net, gemm_mode=mode)
+    ins = MU.input_layers(net)
+    run, out = eng.forward({ins[k]: v for k, v in feed.items()}, win, deterministic=False, train=True, update_bn=False)
+    probs = eng.read(out).reshape(out_ref.shape)
+    rel = np.abs(probs - out_ref).max() / np.abs(out_ref).max()
+    assert rel < 1e-4, (mode, 'probs', rel)
+    assert (probs.argmax(-1) == out_ref.argmax(-1)).all()
+    eng.loss_and_backward(run, out, 'temporal_softmax', y, mask, count=float(mask.sum()))
+    assert abs(eng.read_loss() - loss_ref) < 1e-4 * abs(loss_ref)
+    params = L.get_all_params(net, trainable=True)
+    grads = eng.param_grads(params)
+    gmax = max(np.abs(gr).max() for gr in grads_ref)
+    worst = 0.0
+    for p, g, gr in zip(params, grads, grads_ref):
+        scale = max(np.abs(gr).max(), 2e-2 * gmax)
+        err = np.abs(g - gr).max() / scale
+        worst = max(worst, err)
+        assert err < 2e-3, (mode, p.name, err, scale)
+    print('mode %s: probs rel %.2e, worst grad err %.2e' % (mode, rel, worst))
+
+
 def test_deterministic_eval_and_val_fn_api():
     """The runners' call convention: val_fn(X, mask, X2, window) -> (N,T,C) probabilities."""
     spec, net, feed, mask, y, dm, win = _case('adenet_v2', 5, 'concat')

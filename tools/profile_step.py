@@ -12,7 +12,7 @@ from ipavsr_b200.custom.objectives import temporal_softmax_loss
 from ipavsr_b200.custom.updates import adam
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--mode', default='tf32x3')
+ap.add_argument('--mode', default='f16x3')
 ap.add_argument('--batch', type=int, default=512)
 ap.add_argument('--steps', type=int, default=5)
 args = ap.parse_args()
