@@ -291,7 +291,7 @@ def main():
                       sc.data_ptr() + 12, 0, st)
             run = lambda: _lib.call('ipavsr_gemm_f16x3', 0, 0, M, N, K, ah.data_ptr(), al.data_ptr(), K, sc.data_ptr() + 4,
                                     bh.data_ptr(), bl.data_ptr(), N, sc.data_ptr() + 12, Cm.data_ptr(), N, bias.data_ptr(),
-                                    1, 0, None, st)
+                                    1, 0, None, None, None, 0, st)
         else:
             run = lambda: _lib.call('ipavsr_gemm', mode, 0, 0, M, N, K, A.data_ptr(), K, B.data_ptr(), N, Cm.data_ptr(), N,
                                     bias.data_ptr(), 1, 0, None, 0, st)

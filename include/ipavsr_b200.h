@@ -94,17 +94,20 @@ int ipavsr_f16_split(const float* x, int ldx, int64_t rows, int cols, uint16_t* 
  * amax / exps have nseg entries */
 int ipavsr_f16_split_segments(const float* x, uint16_t* hi, uint16_t* lo, uint64_t n, const int32_t* seg_id, int nseg,
                               float* amax, int32_t* exps, void* stream);
-/* C = act(op(A) op(B) (+C) + bias) on split operands (lda/ldb in halves); amax_out (optional) receives max |C| */
+/* C = act(op(A) op(B) (+C) + bias) on split operands (lda/ldb in halves); amax_out (optional) receives max |C|.
+ * C_hi/C_lo (optional, leading dimension ldc) receive the fp16 split of C under the STATIC scale 2^c_exp — for outputs
+ * with a known bound (sigmoid / tanh: |C| <= 1 -> c_exp = 14) the next GEMM then needs no split pass at all. */
 int ipavsr_gemm_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* A_hi, const uint16_t* A_lo, int lda,
                       const int32_t* expA, const uint16_t* B_hi, const uint16_t* B_lo, int ldb, const int32_t* expB,
-                      float* C, int ldc, const float* bias, int act, int accumulate, float* amax_out, void* stream);
+                      float* C, int ldc, const float* bias, int act, int accumulate, float* amax_out, uint16_t* C_hi,
+                      uint16_t* C_lo, int c_exp, void* stream);
 /* 1 if the fp16 tensor-core path takes this product (16-byte aligned hi/lo, ld % 8 == 0, K >= 16, N >= 8, >= 4 MFLOP) */
 int ipavsr_gemm_f16_supported(int M, int N, int K, const void* A, int lda, const void* B, int ldb);
 
 /* dZ = dY * act'(Y)  and  db[N] (+)= column sums of dZ   (backward of DenseLayer's nonlinearity and bias).
- * dZ may alias dY.  db may be NULL. */
+ * dZ may alias dY.  db may be NULL.  amax (optional, device float, atomically max-combined) receives max |dZ|. */
 int ipavsr_dense_bwd_prep(const float* dY, int lddy, const float* Y, int ldy, float* dZ, int lddz,
-                          float* db, int M, int N, int act, int accumulate_db, void* stream);
+                          float* db, int M, int N, int act, int accumulate_db, float* amax, void* stream);
 /* out[N] (+)= column sums of X[M,N] */
 int ipavsr_colsum(const float* X, int ldx, float* out, int M, int N, int accumulate, void* stream);
 

@@ -32,9 +32,9 @@ _SIGS = {
     'ipavsr_amax': (I, [P, I, I64, I, P, P]),
     'ipavsr_f16_split': (I, [P, I, I64, I, P, P, I, P, P, I, P]),
     'ipavsr_f16_split_segments': (I, [P, P, P, U64, P, I, P, P, P]),
-    'ipavsr_gemm_f16x3': (I, [I, I, I, I, I, P, P, I, P, P, P, I, P, P, I, P, I, I, P, P]),
+    'ipavsr_gemm_f16x3': (I, [I, I, I, I, I, P, P, I, P, P, P, I, P, P, I, P, I, I, P, P, P, I, P]),
     'ipavsr_gemm_f16_supported': (I, [I, I, I, P, I, P, I]),
-    'ipavsr_dense_bwd_prep': (I, [P, I, P, I, P, I, P, I, I, I, I, P]),
+    'ipavsr_dense_bwd_prep': (I, [P, I, P, I, P, I, P, I, I, I, I, P, P]),
     'ipavsr_colsum': (I, [P, I, P, I, I, I, P]),
     'ipavsr_delta_fwd': (I, [P, I, P, I, I, I, I, I, I, P]),
     'ipavsr_delta_bwd': (I, [P, I, P, I, I, I, I, I, I, P]),

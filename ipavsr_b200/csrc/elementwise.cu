@@ -17,13 +17,13 @@ template <bool WITH_ACT>
 __global__ void __launch_bounds__(256) colsum_prep_kernel(const float* __restrict__ dY, int lddy,
                                                           const float* __restrict__ Y, int ldy,
                                                           float* __restrict__ dZ, int lddz, float* __restrict__ db,
-                                                          int M, int N, int act) {
+                                                          int M, int N, int act, float* __restrict__ amax) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   const int r0 = blockIdx.y * PREP_ROWS;
   const int r1 = min(M, r0 + PREP_ROWS);
-  float s = 0.f;
+  float s = 0.f, mx = 0.f;
   if (c < N) {
     for (int r = r0 + rl; r < r1; r += 8) {
       float g = dY[(size_t)r * lddy + c];
@@ -32,7 +32,12 @@ __global__ void __launch_bounds__(256) colsum_prep_kernel(const float* __restric
         dZ[(size_t)r * lddz + c] = g;
       }
       s += g;
+      mx = fmaxf(mx, fabsf(g));
     }
+  }
+  if (amax != nullptr) {
+    mx = warp_max(mx);
+    if (lane == 0 && mx > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(mx));
   }
   if (db == nullptr) return;
   red[rl][lane] = s;
@@ -458,12 +463,12 @@ using namespace ipavsr;
 extern "C" {
 
 int ipavsr_dense_bwd_prep(const float* dY, int lddy, const float* Y, int ldy, float* dZ, int lddz, float* db, int M,
-                          int N, int act, int accumulate_db, void* stream) {
+                          int N, int act, int accumulate_db, float* amax, void* stream) {
   IPAVSR_CHECK_ARG(M >= 0 && N >= 0 && dY && Y && dZ, "bad arguments");
   if (M == 0 || N == 0) return IPAVSR_OK;
   if (db && !accumulate_db) IPAVSR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, S(stream)));
   dim3 grid((N + 31) / 32, (M + PREP_ROWS - 1) / PREP_ROWS);
-  colsum_prep_kernel<true><<<grid, 256, 0, S(stream)>>>(dY, lddy, Y, ldy, dZ, lddz, db, M, N, act);
+  colsum_prep_kernel<true><<<grid, 256, 0, S(stream)>>>(dY, lddy, Y, ldy, dZ, lddz, db, M, N, act, amax);
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }
@@ -474,7 +479,7 @@ int ipavsr_colsum(const float* X, int ldx, float* out, int M, int N, int accumul
   if (!accumulate) IPAVSR_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, S(stream)));
   if (M == 0) return IPAVSR_OK;
   dim3 grid((N + 31) / 32, (M + PREP_ROWS - 1) / PREP_ROWS);
-  colsum_prep_kernel<false><<<grid, 256, 0, S(stream)>>>(X, ldx, nullptr, 0, nullptr, 0, out, M, N, 0);
+  colsum_prep_kernel<false><<<grid, 256, 0, S(stream)>>>(X, ldx, nullptr, 0, nullptr, 0, out, M, N, 0, nullptr);
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }

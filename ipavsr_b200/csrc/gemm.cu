@@ -16,7 +16,8 @@ int gemm_tc_presplit(int transA, int transB, int M, int N, int K, const float* A
 int tf32_split_launch(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 int gemm_tc_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* Ahi, const uint16_t* Alo, int lda,
                   const int32_t* expA, const uint16_t* Bhi, const uint16_t* Blo, int ldb, const int32_t* expB, float* C,
-                  int ldc, const float* bias, int act, int accumulate, float* amax, cudaStream_t st);
+                  int ldc, const float* bias, int act, int accumulate, float* amax, uint16_t* C16hi, uint16_t* C16lo,
+                  int c16_exp, cudaStream_t st);
 bool gemm_tc_f16_supported(int M, int N, int K, const void* A, int lda, const void* B, int ldb);
 int f16_split_launch(const float* x, int ldx, int rows, int cols, uint16_t* hi, uint16_t* lo, int ldo, float* amax,
                      int32_t* exp_out, int amax_ready, cudaStream_t st);
@@ -76,7 +77,7 @@ int ipavsr_gemm(int mode, int transA, int transB, int M, int N, int K, const flo
     if ((rc = f16_split_launch(A, lda, ra, ca, ah, al, lda16, amax, exps, 0, st))) return rc;
     if ((rc = f16_split_launch(B, ldb, rb, cb, bh, bl, ldb16, amax + 1, exps + 1, 0, st))) return rc;
     return gemm_tc_f16x3(transA, transB, M, N, K, ah, al, lda16, exps, bh, bl, ldb16, exps + 1, C, ldc, bias, act,
-                         accumulate, nullptr, st);
+                         accumulate, nullptr, nullptr, nullptr, 0, st);
   }
   set_error("ipavsr_gemm: unknown mode %d", mode);
   return IPAVSR_ERR_ARG;
@@ -88,16 +89,20 @@ int ipavsr_gemm_f16_supported(int M, int N, int K, const void* A, int lda, const
 
 int ipavsr_gemm_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* A_hi, const uint16_t* A_lo, int lda,
                       const int32_t* expA, const uint16_t* B_hi, const uint16_t* B_lo, int ldb, const int32_t* expB,
-                      float* C, int ldc, const float* bias, int act, int accumulate, float* amax_out, void* stream) {
+                      float* C, int ldc, const float* bias, int act, int accumulate, float* amax_out, uint16_t* C_hi,
+                      uint16_t* C_lo, int c_exp, void* stream) {
   IPAVSR_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "negative size");
   IPAVSR_CHECK_ARG(A_hi && A_lo && B_hi && B_lo && C && expA && expB, "null pointer");
+  IPAVSR_CHECK_ARG((C_hi == nullptr) == (C_lo == nullptr) && c_exp >= -126 && c_exp <= 126, "bad C_hi / C_lo / c_exp");
+  IPAVSR_CHECK_ARG(C_hi == nullptr || (ldc % 4 == 0 && ((reinterpret_cast<uintptr_t>(C_hi) | reinterpret_cast<uintptr_t>(C_lo)) & 7) == 0),
+                   "C_hi / C_lo need 8-byte alignment and ldc % 4 == 0");
   IPAVSR_CHECK_ARG(act >= IPAVSR_ACT_LINEAR && act <= IPAVSR_ACT_ELU, "unknown nonlinearity code");
   IPAVSR_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "leading dimension too small");
   IPAVSR_CHECK_ARG(gemm_tc_f16_supported(M, N, K, A_hi, lda, B_hi, ldb) && gemm_tc_f16_supported(M, N, K, A_lo, lda, B_lo, ldb),
                    "shape/alignment not supported by the fp16 tensor-core path (see ipavsr_gemm_f16_supported)");
   if (M == 0 || N == 0) return IPAVSR_OK;
   return gemm_tc_f16x3(transA, transB, M, N, K, A_hi, A_lo, lda, expA, B_hi, B_lo, ldb, expB, C, ldc, bias, act,
-                       accumulate, amax_out, reinterpret_cast<cudaStream_t>(stream));
+                       accumulate, amax_out, C_hi, C_lo, c_exp, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ipavsr_gemm_tc_supported(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,

@@ -23,6 +23,7 @@
 // [32 k-rows x 32 floats] (TMA swizzle 128B_ATOM_32B) and is consumed through MN-major UMMA descriptors
 // (SWIZZLE_128B_BASE32B) — no transposed copies are made.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -232,6 +233,9 @@ struct TcParams {
   const int32_t* expA;   // f16 mode: per-tensor scale exponents of the operands (device), result *= 2^-(eA+eB)
   const int32_t* expB;
   float* amax;           // optional (device): atomic max of |C| over the written elements (feeds the next fp16 split)
+  uint16_t* C16hi;       // optional: fp16 hi/lo split of C with the STATIC scale 2^c16_exp (outputs with a known bound,
+  uint16_t* C16lo;       //           e.g. sigmoid/tanh: |C| <= 1 -> exponent 14), same leading dimension as C
+  int c16_exp;
   unsigned long long* dbg;   // optional (device): per-CTA phase timestamps (globaltimer ns), see tools/gemm_phases.py
 };
 
@@ -540,6 +544,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) tile_max = fmaxf(tile_max, fabsf(v[j]));
           }
+          if (p.C16hi != nullptr) {
+            const float sc = __int_as_float((127 + p.c16_exp) << 23);
+            const size_t off = (size_t)row * p.ldc + n0 + c0;
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              __half h[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float xs = v[j4 + j] * sc;
+                h[j] = __float2half_rn(xs);
+                l[j] = __float2half_rn((xs - __half2float(h[j])) * 2048.0f);
+              }
+              *reinterpret_cast<uint2*>(p.C16hi + off + j4) = *reinterpret_cast<const uint2*>(h);
+              *reinterpret_cast<uint2*>(p.C16lo + off + j4) = *reinterpret_cast<const uint2*>(l);
+            }
+          }
           if (p.Chi != nullptr) {
             const size_t off = (size_t)row * p.ldc + n0 + c0;
 #pragma unroll
@@ -629,6 +649,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 *reinterpret_cast<float4*>(p.Chi + off) = h;
                 *reinterpret_cast<float4*>(p.Clo + off) = l;
               }
+              if (p.C16hi != nullptr) {
+                const float sc = __int_as_float((127 + p.c16_exp) << 23);
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float xs = ov[j] * sc;
+                  const __half h = __float2half_rn(xs);
+                  reinterpret_cast<__half*>(p.C16hi)[(size_t)row * p.ldc + col + j] = h;
+                  reinterpret_cast<__half*>(p.C16lo)[(size_t)row * p.ldc + col + j] =
+                      __float2half_rn((xs - __half2float(h)) * 2048.0f);
+                }
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
@@ -644,6 +676,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     tf32_hi_lo(o, h, l);
                     p.Chi[(size_t)row * p.ldc + col + j] = h;
                     p.Clo[(size_t)row * p.ldc + col + j] = l;
+                  }
+                  if (p.C16hi != nullptr) {
+                    const float xs = o * __int_as_float((127 + p.c16_exp) << 23);
+                    const __half h = __float2half_rn(xs);
+                    reinterpret_cast<__half*>(p.C16hi)[(size_t)row * p.ldc + col + j] = h;
+                    reinterpret_cast<__half*>(p.C16lo)[(size_t)row * p.ldc + col + j] =
+                        __float2half_rn((xs - __half2float(h)) * 2048.0f);
                   }
                 }
             }
@@ -806,7 +845,7 @@ int amax_launch(const float* x, int ldx, int rows, int cols, float* amax, cudaSt
 static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, const void* Ahi, const void* Alo, int lda,
                         const void* Bhi, const void* Blo, int ldb, float* C, int ldc, const float* bias, int act,
                         int accumulate, float* Chi, float* Clo, const int32_t* expA, const int32_t* expB, float* amax,
-                        cudaStream_t st) {
+                        cudaStream_t st, uint16_t* C16hi = nullptr, uint16_t* C16lo = nullptr, int c16_exp = 0) {
   const bool x3 = kind != 0, f16 = kind == 2;
   const bool a_mn = transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;     // B stored [K,N]: N contiguous
@@ -841,10 +880,11 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
   p.Chi = Chi; p.Clo = Clo; p.expA = expA; p.expB = expB; p.amax = amax;
   p.dbg = g_gemm_dbg;
+  p.C16hi = C16hi; p.C16lo = C16lo; p.c16_exp = c16_exp;
   const int num_kb = (K + bke - 1) / bke;
   const int tiles = ((M + TC_BM * cg - 1) / (TC_BM * cg)) * cg * ((N + BN - 1) / BN);
   int splits = 1;
-  if (act == IPAVSR_ACT_LINEAR && Chi == nullptr) {
+  if (act == IPAVSR_ACT_LINEAR && Chi == nullptr && C16hi == nullptr) {
     if (tiles * 2 <= sm_count() && num_kb >= 32 && amax == nullptr) {         // fill the machine for skinny outputs
       splits = sm_count() / tiles;
       if (splits > num_kb / 8) splits = num_kb / 8;
@@ -919,9 +959,10 @@ int gemm_tc_presplit(int transA, int transB, int M, int N, int K, const float* A
 // fp16 three-product GEMM on operands split by f16split.cu (hi/lo fp16 arrays, leading dimensions in halves)
 int gemm_tc_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* Ahi, const uint16_t* Alo, int lda,
                   const int32_t* expA, const uint16_t* Bhi, const uint16_t* Blo, int ldb, const int32_t* expB, float* C,
-                  int ldc, const float* bias, int act, int accumulate, float* amax, cudaStream_t st) {
+                  int ldc, const float* bias, int act, int accumulate, float* amax, uint16_t* C16hi, uint16_t* C16lo,
+                  int c16_exp, cudaStream_t st) {
   return gemm_tc_core(2, transA, transB, M, N, K, Ahi, Alo, lda, Bhi, Blo, ldb, C, ldc, bias, act, accumulate, nullptr,
-                      nullptr, expA, expB, amax, st);
+                      nullptr, expA, expB, amax, st, C16hi, C16lo, c16_exp);
 }
 
 bool gemm_tc_f16_supported(int M, int N, int K, const void* A, int lda, const void* B, int ldb) {

@@ -193,14 +193,19 @@ class _Profiler(object):
     """Optional per-entry-point device timing (IPAVSR_PROFILE=1): CUDA events around every C-ABI call, summed by
     entry-point name.  Off by default (it adds event overhead); used by tools/profile_step.py."""
 
-    def __init__(self):
+    def __init__(self, by_shape=False):
         self.events = []
+        self.by_shape = by_shape
 
     def call(self, name, *args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(getattr(_lib.load(), name)(*args), name)
         e1.record()
+        if self.by_shape and name.startswith('ipavsr_gemm'):
+            # (transA, transB, M, N, K) lead the argument list of every GEMM entry point except ipavsr_gemm (mode first)
+            a = args[1:6] if name == 'ipavsr_gemm' else args[0:5]
+            name = '%s ta=%d tb=%d %dx%dx%d' % ((name,) + tuple(int(x) for x in a))
         self.events.append((name, e0, e1))
 
     def summary(self):
@@ -261,6 +266,11 @@ class Engine(object):
         self.concurrent_lstm = os.environ.get('IPAVSR_CONCURRENT_LSTM', '1') != '0'
         self._side = []
         self._side_next = 0
+        self._copy_stream = None
+        self._c14 = None
+        # fp16 hi/lo of sigmoid/tanh outputs written by the GEMM epilogue itself (static scale 2^14).  Off by default: with
+        # the epilogue's row-per-thread store pattern the extra 8-byte stores cost more than the separate split pass saves.
+        self.epilogue_split = os.environ.get('IPAVSR_EPILOGUE_SPLIT', '0') == '1'
 
     # ------------------------------------------------------------------------------------------------
     # small helpers
@@ -347,6 +357,15 @@ class Engine(object):
             self._split_cache[key] = hit
         return hit[0], hit[1]
 
+    def _const14(self):
+        """[amax = 1.0, exponent = 14] for tensors bounded by 1 (sigmoid / tanh activations, LSTM hidden states)."""
+        if self._c14 is None:
+            t = torch.zeros(2, dtype=torch.float32, device=self.device)
+            t[0] = 1.0
+            t[1:2].view(torch.int32)[0] = 14
+            self._c14 = t
+        return self._c14
+
     def _split16(self, m):
         """fp16x3 operand of a float32 DevMat: (hi ptr, lo ptr, exponent ptr); leading dimension = m.ld halves."""
         ar = self.arena
@@ -378,14 +397,25 @@ class Engine(object):
             else:
                 ah, al, ea = self._split16(A)
                 bh, bl, eb = self._split16(B)
-                amax = None
+                amax = chi = clo = None
                 if emit_split and not accumulate:
-                    # the epilogue leaves max|C| behind, so the split of C (first use as an operand) needs no reduction pass
-                    t = torch.zeros(2, dtype=torch.float32, device=self.device)
-                    self._amax[(Cm.ptr, Cm.rows, Cm.cols, Cm.ld)] = t
-                    amax = t.data_ptr()
+                    key = (Cm.ptr, Cm.rows, Cm.cols, Cm.ld)
+                    if act in (1, 3) and self.epilogue_split:
+                        # sigmoid / tanh outputs are bounded by 1: the epilogue writes the fp16 hi/lo split itself under
+                        # the static scale 2^14, and no split pass is needed at all
+                        n = max(Cm.rows * Cm.ld, 8)
+                        hi = torch.empty(n, dtype=torch.float16, device=self.device)
+                        lo = torch.empty(n, dtype=torch.float16, device=self.device)
+                        self._split_cache[key] = (hi, lo, self._const14(), Cm.t)
+                        chi, clo = hi.data_ptr(), lo.data_ptr()
+                    else:
+                        # the epilogue leaves max|C| behind, so the split of C (first use as an operand) needs no
+                        # reduction pass
+                        t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                        self._amax[key] = t
+                        amax = t.data_ptr()
                 _lib.call('ipavsr_gemm_f16x3', transA, transB, M, N, K, ah, al, A.ld, ea, bh, bl, B.ld, eb,
-                          Cm.ptr, Cm.ld, bias, act, accumulate, amax, self.stream)
+                          Cm.ptr, Cm.ld, bias, act, accumulate, amax, chi, clo, 14, self.stream)
                 return
         if mode != 0 and not self.lib.ipavsr_gemm_tc_supported(transA, transB, M, N, K, A.ptr, A.ld, B.ptr, B.ld,
                                                                 Cm.ptr, Cm.ld):
@@ -446,6 +476,31 @@ class Engine(object):
         d[:, :F].copy_(t.reshape(N * T, F), non_blocking=True)
         return DevMat(d, d.data_ptr(), N * T, F, ld)
 
+    def _stage_inputs(self, inputs):
+        """Host inputs are copied on a dedicated copy stream, all issued up front in graph order, so that the upload of
+        the later streams overlaps the encoder of the first ones; the compute stream waits per input, on first use.
+        Pinned host tensors make the copies truly asynchronous.  Returns {layer: (device value, event)}."""
+        host = [l for l in self.input_layers
+                if not (isinstance(inputs[l], torch.Tensor) and inputs[l].is_cuda)]
+        if not host or os.environ.get('IPAVSR_COPY_STREAM', '1') == '0':
+            return {}
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        cs = self._copy_stream
+        cs.wait_stream(main)            # buffers recycled by the allocator may still be read by earlier kernels
+        staged = {}
+        # the mask first (tiny, needed by every LSTM), then the streams in graph order
+        order = [l for l in host if l in self.mask_layers] + [l for l in host if l not in self.mask_layers]
+        with torch.cuda.stream(cs):
+            for l in order:
+                val = self._upload(inputs[l], 'mask' if l in self.mask_layers else 'float')
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                (val if isinstance(val, torch.Tensor) else val.t).record_stream(main)
+                staged[l] = (val, ev)
+        return staged
+
     # ------------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------------
@@ -459,6 +514,7 @@ class Engine(object):
                 break
         N, T = int(first.shape[0]), int(first.shape[1])
         run = _Run(N, T)
+        staged = self._stage_inputs(inputs)
         self._split_cache = {}
         self._amax = {}
         if self.gemm_mode in (1, 4):
@@ -471,7 +527,11 @@ class Engine(object):
                 if i is not None and i in run.pending and not (isinstance(l, L.LSTMLayer) and i in self.mask_layers):
                     self._wait(run, i)
             if isinstance(l, L.InputLayer):
-                if l in self.mask_layers:
+                if l in staged:
+                    val, ev = staged[l]
+                    torch.cuda.current_stream(self.device).wait_event(ev)
+                    run.vals[l] = val if l in self.mask_layers else [val]
+                elif l in self.mask_layers:
                     run.vals[l] = self._upload(inputs[l], 'mask')
                 else:
                     run.vals[l] = [self._upload(inputs[l], 'float')]
@@ -581,6 +641,15 @@ class Engine(object):
                 run.keep.append(xw)
                 run.saved[l] = (mask, gates, cell, hprev)
                 run.vals[l] = [out]
+                if self.gemm_mode == 4:
+                    # h = o * tanh(c) lies in (-1, 1); padded / first steps carry hid_init: |out|, |hprev| <= max(1, |hid_init|)
+                    # is known without a pass over the (N*T, H) tensors
+                    bound = torch.zeros(2, dtype=torch.float32, device=self.device)
+                    bound[0] = 1.0
+                    _lib.call('ipavsr_amax', ar.mat((l, 'hid_init')).ptr, H, 1, H, bound.data_ptr(), st)
+                    self._amax[(out.ptr, out.rows, out.cols, out.ld)] = bound
+                    if hprev is not None:
+                        self._amax[(hprev.ptr, hprev.rows, hprev.cols, hprev.ld)] = bound.clone()
             elif isinstance(l, (L.ElemwiseSumLayer, L.AdaptiveElemwiseSumLayer)):
                 ins = [self._single(run.vals[i]) for i in l.input_layers]
                 rows, F = ins[0].rows, ins[0].cols
@@ -687,8 +756,15 @@ class Engine(object):
                 else:
                     dZ = dY if run.grads[l][1] else self.new(rows, Nout)
                     y = run.vals[l][0]
+                    amax = None
+                    if self.gemm_mode == 4:
+                        self._split_cache.pop((dZ.ptr, dZ.rows, dZ.cols, dZ.ld), None)     # dY's split (if any) is stale
+                        t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                        self._amax[(dZ.ptr, dZ.rows, dZ.cols, dZ.ld)] = t
+                        amax = t.data_ptr()
                     _lib.call('ipavsr_dense_bwd_prep', dY.ptr, dY.ld, y.ptr, y.ld, dZ.ptr, dZ.ld,
-                              G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0, st)
+                              G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0,
+                              amax, st)
                 self._proj_bwd(run, l.input_layer, xin, dZ, ar.mat((l, 'W')), G((l, 'W')))
             elif isinstance(l, L.BatchNormLayer):
                 dy = gsegs[0]

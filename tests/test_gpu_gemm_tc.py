@@ -114,7 +114,7 @@ def test_f16x3_presplit_api_and_amax():
     assert (np.abs(rec - A)[big] <= np.abs(A)[big] * 2.0 ** -21).all()
     dC = G.zeros((M, N))
     G.call('ipavsr_gemm_f16x3', 0, 0, M, N, K, ah.data_ptr(), al.data_ptr(), K, exps.data_ptr(), bh.data_ptr(),
-           bl.data_ptr(), N, exps.data_ptr() + 4, dC.data_ptr(), N, None, 0, 0, amax.data_ptr() + 8, G.stream())
+           bl.data_ptr(), N, exps.data_ptr() + 4, dC.data_ptr(), N, None, 0, 0, amax.data_ptr() + 8, None, None, 0, G.stream())
     ref = A.astype(np.float64) @ B.astype(np.float64)
     got = G.host(dC)
     # error relative to the natural scale of each dot product (sum of |a||b|)

@@ -221,9 +221,11 @@ def test_dense_bwd_prep_and_colsum(act):
     ld = 204
     pad = lambda a: np.pad(a, ((0, 0), (0, ld - N)))
     d_dy, d_y, d_dz, d_db = G.dev(pad(dy)), G.dev(pad(y)), G.zeros((M, ld)), G.zeros((N,))
+    d_amax = G.zeros((1,))
     G.call('ipavsr_dense_bwd_prep', d_dy.data_ptr(), ld, d_y.data_ptr(), ld, d_dz.data_ptr(), ld, d_db.data_ptr(), M, N,
-           act, 0, G.stream())
+           act, 0, d_amax.data_ptr(), G.stream())
     assert G.relerr(G.host(d_dz)[:, :N], want) < 3e-6
+    assert G.host(d_amax)[0] == np.abs(G.host(d_dz)[:, :N]).max()
     assert G.relerr(G.host(d_db), want.sum(0)) < 1e-5
     G.call('ipavsr_colsum', d_dy.data_ptr(), ld, d_db.data_ptr(), M, N, 0, G.stream())
     assert G.relerr(G.host(d_db), dy.astype(np.float64).sum(0)) < 1e-5

@@ -28,7 +28,7 @@ for name, ta, tb, M, N, K in (('fc1 fwd', 0, 0, 20480, 2000, 1200), ('fc2 fwd', 
     _lib.call('ipavsr_f16_split', A.data_ptr(), lda, A.shape[0], A.shape[1], ah.data_ptr(), al.data_ptr(), lda, amax.data_ptr(), exps.data_ptr(), 0, st())
     _lib.call('ipavsr_f16_split', B.data_ptr(), ldb, B.shape[0], B.shape[1], bh.data_ptr(), bl.data_ptr(), ldb, amax.data_ptr() + 4, exps.data_ptr() + 4, 0, st())
     ms = timeit(lambda: _lib.call('ipavsr_gemm_f16x3', ta, tb, M, N, K, ah.data_ptr(), al.data_ptr(), lda, exps.data_ptr(), bh.data_ptr(), bl.data_ptr(), ldb,
-                                  exps.data_ptr() + 4, Cm.data_ptr(), N, bias.data_ptr(), 1 if not ta else 0, 0, None, st()))
+                                  exps.data_ptr() + 4, Cm.data_ptr(), N, bias.data_ptr(), 1 if not ta else 0, 0, None, None, None, 0, st()))
     fl = 2.0 * M * N * K
     fh, fl32 = torch.empty_like(A), torch.empty_like(A); gh, gl = torch.empty_like(B), torch.empty_like(B)
     _lib.call('ipavsr_tf32_split_rna', A.data_ptr(), fh.data_ptr(), fl32.data_ptr(), A.numel(), st())

@@ -20,7 +20,7 @@ if kind == 'f16':
     _lib.call('ipavsr_f16_split', A.data_ptr(), lda, A.shape[0], A.shape[1], ah.data_ptr(), al.data_ptr(), lda, amax.data_ptr(), exps.data_ptr(), 0, st())
     _lib.call('ipavsr_f16_split', B.data_ptr(), ldb, B.shape[0], B.shape[1], bh.data_ptr(), bl.data_ptr(), ldb, amax.data_ptr() + 4, exps.data_ptr() + 4, 0, st())
     run = lambda: _lib.call('ipavsr_gemm_f16x3', ta, tb, M, N, K, ah.data_ptr(), al.data_ptr(), lda, exps.data_ptr(), bh.data_ptr(), bl.data_ptr(), ldb,
-                            exps.data_ptr() + 4, Cm.data_ptr(), N, bias.data_ptr() if USE_BIAS else None, ACT, 0, None, st())
+                            exps.data_ptr() + 4, Cm.data_ptr(), N, bias.data_ptr() if USE_BIAS else None, ACT, 0, None, None, None, 0, st())
 else:
     ah, al, bh, bl = torch.empty_like(A), torch.empty_like(A), torch.empty_like(B), torch.empty_like(B)
     _lib.call('ipavsr_tf32_split_rna', A.data_ptr(), ah.data_ptr(), al.data_ptr(), A.numel(), st())

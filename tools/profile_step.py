@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--mode', default='f16x3')
 ap.add_argument('--batch', type=int, default=512)
 ap.add_argument('--steps', type=int, default=5)
+ap.add_argument('--by-shape', action='store_true', help='list GEMMs per shape')
 args = ap.parse_args()
 net, v, mask_var, window = bench.build_network()
 eng = E.get_engine(net, gemm_mode=args.mode)
@@ -28,7 +29,7 @@ dx = [torch.from_numpy(x).cuda() for x in xs]
 dmask, dy = torch.from_numpy(mask).cuda(), torch.from_numpy(y).cuda()
 for _ in range(3):
     train(dx[0], dx[1], dx[2], dy, dmask, bench.THETA)
-prof = E._Profiler()
+prof = E._Profiler(by_shape=args.by_shape)
 orig = _lib.call
 _lib.call = prof.call
 E._lib.call = prof.call
@@ -45,6 +46,6 @@ rows = sorted(summ.items(), key=lambda kv: -kv[1][1])
 print('mode %s batch %d: %.2f ms/step (with event overhead)' % (args.mode, args.batch, total))
 acc = 0.0
 for name, (n, t) in rows:
-    print('  %-34s n/step=%6.1f  %8.3f ms/step  %5.1f%%' % (name, n / args.steps, t / args.steps, 100 * t / args.steps / total))
+    print('  %-58s n/step=%6.1f  %8.3f ms/step  %5.1f%%' % (name, n / args.steps, t / args.steps, 100 * t / args.steps / total))
     acc += t / args.steps
 print('  %-34s %26.3f ms/step' % ('(sum of kernels)', acc))
