@@ -145,6 +145,14 @@ int ipavsr_lstm_bwd(const float* dout, const float* w_hid, const float* peep, co
                     int N, int T, int H, int ldh, int backwards, float clip, int accumulate, int impl,
                     void* workspace, uint64_t workspace_bytes, void* stream);
 uint64_t ipavsr_lstm_workspace_bytes(int N, int T, int H);
+/* Tensor-core form of ipavsr_lstm_fwd (same arguments and results) for H <= 256, T <= 64: the recurrent product runs as
+ * fp16 three-product tcgen05 MMAs (fp32 parity, as IPAVSR_GEMM_F16X3).  whid_hi/whid_lo/whid_exp are the fp16 split of
+ * the gate-interleaved W_hid (H rows x 4H columns, leading dimension ldw halves) from ipavsr_f16_split(_segments). */
+int ipavsr_lstm_fwd_f16(const float* xw, const uint16_t* whid_hi, const uint16_t* whid_lo, const int32_t* whid_exp,
+                        int ldw, const float* peep, const float* cell_init, const float* hid_init, const uint8_t* mask,
+                        float* out, float* gates, float* cell, float* hprev, int N, int T, int H, int ldh, int backwards,
+                        void* stream);
+int ipavsr_lstm_fwd_f16_supported(int N, int T, int H, int ldw);
 
 /* ---- a4/a5/a7: fusion, merge, slice, dropout ---------------------------------------------------------- */
 /* out[M,F] = sum_s coeff_s * in_s[M,F]   (ElemwiseSumLayer; AdaptiveElemwiseSumLayer custom/layers.py:178-228).
@@ -231,6 +239,9 @@ int ipavsr_deltas_fir(const float* x, int ldx, double* y, int ldy, const int64_t
 /* profiling aid: when buf != NULL every tensor-core GEMM CTA writes 8 uint64 globaltimer stamps to
  * buf[8 * linear_cta_id ...] = {start, setup done, first stage landed, last MMA issued, accumulator ready, epilogue done} */
 int ipavsr_debug_gemm_timestamps(unsigned long long* buf);
+/* likewise for ipavsr_lstm_fwd_f16: CTA 0 writes its accumulated SM-clock cycles {control: wait-for-h, MMA issue;
+ * epilogue thread 0: wait-for-accumulator, TMEM loads, transpose + cell update + stores, push of h} */
+int ipavsr_debug_lstm_timestamps(unsigned long long* buf);
 
 /* ---- helpers ------------------------------------------------------------------------------------------ */
 int ipavsr_fill(float* p, uint64_t n, float v, void* stream);

@@ -41,6 +41,8 @@ _SIGS = {
     'ipavsr_lstm_fwd': (I, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, U64, P]),
     'ipavsr_lstm_bwd': (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, I, P, U64, P]),
     'ipavsr_lstm_workspace_bytes': (U64, [I, I, I]),
+    'ipavsr_lstm_fwd_f16': (I, [P, P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, I, I, P]),
+    'ipavsr_lstm_fwd_f16_supported': (I, [I, I, I, I]),
     'ipavsr_fuse_sum': (I, [P, P, I, P, P, I, I, I, P]),
     'ipavsr_adasum_bwd_coeff': (I, [P, I, P, P, I, P, I, I, I, P]),
     'ipavsr_copy2d': (I, [P, I, P, I, I, I, P, I, P]),
@@ -62,6 +64,7 @@ _SIGS = {
     'ipavsr_diff_image': (I, [P, I, P, I, P, I, I, P]),
     'ipavsr_deltas_fir': (I, [P, I, P, I, P, I, I, I, I, P]),
     'ipavsr_debug_gemm_timestamps': (I, [P]),
+    'ipavsr_debug_lstm_timestamps': (I, [P]),
     'ipavsr_fill': (I, [P, U64, F, P]),
     'ipavsr_tf32_split': (I, [P, P, P, U64, P]),
 }

@@ -1,0 +1,558 @@
+// Masked Lasagne-LSTM recurrence on the tensor cores (forward), fp32-parity three-product fp16 arithmetic.
+//
+// Same semantics as lstm.cu (reference custom/layers.py:10-80 -> lasagne LSTMLayer); this is
+// the fast path for H <= 256 when the fp16 hi/lo split of W_hid is available (engine mode f16x3).  The FFMA kernel in
+// lstm.cu is bound by the shared-memory -> register return path (13-16 us per time step); here the per-step product
+//     g^T[128 gate columns, 32 utterances] = W_hid^T[128, K] * h^T[K, 32]
+// is 48 tcgen05.mma (kind::f16, M=128, N=32, K=16; lo*hi + hi*lo -> cross accumulator, hi*hi -> main accumulator, as in
+// gemm_tc.cu) issued by one thread, with the accumulators in TMEM.
+//
+// A cluster of CS = ceil(H/32) CTAs owns a tile of 32 utterances for all T steps.  CTA r owns hidden units
+// [32r, 32r+32), i.e. gate columns [128r, 128r+128) of the gate-interleaved W_hid:
+//   * its W_hid^T slice (fp16 hi and lo, 2 x 64 KB at K = 256) is loaded ONCE by TMA, straight from the engine's fp16
+//     split of the parameter arena (MN-major SWIZZLE_128B operand: no transposed copy), and stays in shared memory;
+//   * h_t (fp16 hi/lo, scale 2^eH with eH from max(1, |hid_init|)) lives in a double-buffered K-major SWIZZLE_64B
+//     operand tile; after the cell update every CTA converts its 32 units x 32 utterances of h_{t+1} into that layout
+//     in a staging buffer and pushes it into the next-step tile of all CS CTAs with cp.async.bulk
+//     (shared::cta -> shared::cluster), completing on the destination's mbarrier (complete_tx) — the MMA thread of each
+//     CTA simply waits for CS x 4 KB to land: there is no cluster barrier in the time loop;
+//   * 128 epilogue threads own one TMEM lane each (gate column 4u+g): tcgen05.ld, add the hoisted input projection
+//     xw[t] (coalesced: a warp reads 32 consecutive gate columns of one frame), a 4x4 shuffle transpose brings the four
+//     gates of a (unit, utterance) cell into one thread, which then owns 8 cells.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace ipavsr {
+
+namespace {
+
+constexpr int QN = 32;            // utterances per cluster tile (MMA N)
+constexpr int QU = 32;            // hidden units per CTA (128 gate columns = MMA M)
+constexpr int QTHREADS = 288;     // warps 0-7: epilogue (TMEM lane quadrant w%4, utterance half w/4); warp 8: TMA / MMA
+constexpr int QEPI = 256;         // epilogue threads
+constexpr int QC = 16;            // utterances (TMEM columns) per epilogue thread
+// The tensor core adds into its fp32 TMEM accumulator with truncation (gemm_tc.cu), a bias that compounds over the T
+// recurrent steps.  The hi*hi products are therefore spread over QACC accumulators (two k-steps = 32 hidden units
+// each at H <= 256) that the epilogue sums with round-to-nearest; the tiny cross terms share one accumulator.
+constexpr int QACC = 8;
+constexpr int QCROSS = 2;         // cross-term accumulators (alternating k-steps): halves the dependent MMA chain
+constexpr int QTMEM_COLS = 512;   // (QACC + QCROSS) * 32 = 320 columns, allocated as the next power of two
+
+__device__ __forceinline__ uint32_t q_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void q_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(q_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void q_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(q_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void q_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "Q_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra Q_DONE;\n"
+      "bra Q_WAIT;\n"
+      "Q_DONE:\n"
+      "}\n" ::"r"(q_smem(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t q_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ uint32_t q_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t q_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void q_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void q_tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          q_smem(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(q_smem(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// shared::cta -> (remote) shared::cluster bulk copy, completing `bytes` on the destination CTA's mbarrier
+__device__ __forceinline__ void q_bulk_s2s(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void q_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void q_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(q_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void q_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void q_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void q_tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void q_tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (see gemm_tc.cu): layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t q_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// byte offset of element (row = utterance j, k-in-chunk c in 0..31) inside one 32 x 64-byte SWIZZLE_64B chunk
+__device__ __forceinline__ uint32_t q_sw64(int j, int c) {
+  return (uint32_t)(j * 64 + ((((c >> 3) ^ ((j >> 1) & 3)) & 3) << 4) + ((c & 7) << 1));
+}
+
+// sigmoid / tanh from ex2.approx + rcp.approx (<= 2 ulp each): ~3e-7 relative for sigmoid; tanh as 1 - 2 / (e^{2x} + 1)
+// with an odd polynomial below |x| = 0.15 (where that form cancels): absolute error < 2e-7 everywhere.  Saturates
+// correctly at +-inf.  (The FFMA kernel in lstm.cu keeps libm's expf / tanhf.)
+__device__ __forceinline__ float q_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float q_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float q_sigmoid(float x) { return q_rcp(1.0f + q_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float q_tanh(float x) {
+  const float x2 = x * x;
+  const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.133333333f), -0.333333333f), 1.0f);
+  const float big = 1.0f - 2.0f * q_rcp(1.0f + q_ex2(2.8853900817779268f * x));
+  return fabsf(x) < 0.15f ? poly : big;
+}
+
+struct CellF {
+  float i, f, cin, o, c, h;
+};
+__device__ __forceinline__ CellF q_cell(float gi, float gf, float gc, float go, float c_prev, float h_prev, bool m,
+                                        bool has_peep, float w_ci, float w_cf, float w_co) {
+  CellF r;
+  if (has_peep) {
+    gi = fmaf(c_prev, w_ci, gi);
+    gf = fmaf(c_prev, w_cf, gf);
+  }
+  r.i = q_sigmoid(gi);
+  r.f = q_sigmoid(gf);
+  r.cin = q_tanh(gc);
+  const float c_u = r.f * c_prev + r.i * r.cin;
+  if (has_peep) go = fmaf(c_u, w_co, go);
+  r.o = q_sigmoid(go);
+  const float h_u = r.o * q_tanh(c_u);
+  r.c = m ? c_u : c_prev;
+  r.h = m ? h_u : h_prev;
+  return r;
+}
+
+__device__ __forceinline__ long long q_clock() { return clock64(); }
+}  // namespace
+
+unsigned long long* g_lstm_dbg = nullptr;      // profiling aid (ipavsr_debug_lstm_timestamps)
+
+__global__ void __launch_bounds__(QTHREADS, 1)
+lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
+                   const float* __restrict__ xw, const int32_t* __restrict__ w_exp, const float* __restrict__ peep,
+                   const float* __restrict__ cell_init, const float* __restrict__ hid_init,
+                   const uint8_t* __restrict__ mask, float* __restrict__ out, float* __restrict__ gates,
+                   float* __restrict__ cell, float* __restrict__ hprev, int N, int T, int H, int ldh, int backwards,
+                   unsigned long long* dbg) {
+  const int CS = (int)q_cluster_size();
+  const int rank = (int)q_cluster_rank();
+  const int tile = blockIdx.x / CS;
+  const int H4 = 4 * H;
+  const int KB = (CS * QU + 63) / 64;                  // 64-row k-boxes of the W operand
+  const int KSTEPS = CS * 2;                           // MMA k-steps of 16
+  const uint32_t WBYTES = (uint32_t)KB * 16384u;       // one W array (hi or lo): KB boxes x {2 m-boxes x 8 KB}
+  const uint32_t HBYTES = (uint32_t)CS * 2048u;        // one h array (hi or lo) of one buffer: CS chunks of 32 x 64 B
+
+  extern __shared__ uint8_t q_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(q_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sWhi = smem;
+  uint8_t* sWlo = sWhi + WBYTES;
+  uint8_t* sH = sWlo + WBYTES;                         // [2 buffers][hi | lo][CS chunks][2048]
+  uint8_t* sStage = sH + 4 * HBYTES;                   // [2][hi 2048 | lo 2048]
+  __shared__ __align__(8) uint64_t hbar[2], accbar, wbar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_red[4];
+  __shared__ int s_eh;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    q_mbar_init(&hbar[0], 1);
+    q_mbar_init(&hbar[1], 1);
+    q_mbar_init(&accbar, 1);
+    q_mbar_init(&wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(q_smem(&tmem_base_smem)),
+                 "r"((uint32_t)QTMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // scale exponent of the h operand: |h_t| <= max(1, max|hid_init|)
+  if (warp < 4) {
+    float mx = 1.0f;
+    for (int k = tid; k < H; k += 128) mx = fmaxf(mx, fabsf(hid_init[k]));
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+  }
+  q_fence_before();
+  __syncthreads();
+  q_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (tid == 0) {
+    const float mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    s_eh = 14 - ilogbf(mx);
+    // W_hid^T slice: gate columns [128 rank, +128) x all k, straight from the fp16 split of the parameter arena
+    q_mbar_expect_tx(&wbar, 2 * WBYTES);
+    for (int kb = 0; kb < KB; ++kb)
+      for (int mb = 0; mb < 2; ++mb) {
+        q_tma_load_2d(sWhi + (size_t)(kb * 2 + mb) * 8192, &mapWhi, &wbar, rank * 128 + mb * 64, kb * 64);
+        q_tma_load_2d(sWlo + (size_t)(kb * 2 + mb) * 8192, &mapWlo, &wbar, rank * 128 + mb * 64, kb * 64);
+      }
+  }
+  __syncthreads();
+  const int eh = s_eh;
+  const float hs = __int_as_float((127 + eh) << 23);   // 2^eH
+  // h_0 = hid_init for every utterance of the tile (buffer 0, all CS chunks), written by every CTA for itself
+  {
+    const int Kpad = CS * QU;
+    for (int i = tid; i < QN * Kpad; i += QTHREADS) {
+      const int j = i / Kpad, k = i - j * Kpad;
+      const float xs = (k < H ? hid_init[k] : 0.f) * hs;
+      const __half hi = __float2half_rn(xs);
+      const __half lo = __float2half_rn((xs - __half2float(hi)) * 2048.0f);
+      const uint32_t off = (uint32_t)(k >> 5) * 2048u + q_sw64(j, k & 31);
+      *reinterpret_cast<__half*>(sH + off) = hi;
+      *reinterpret_cast<__half*>(sH + HBYTES + off) = lo;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  q_cluster_sync();      // every CTA's barriers are initialised before any remote copy can complete on them
+
+  if (warp == 8) {
+    // ===================== control warp: one thread issues the MMAs =====================
+    if (lane == 0) {
+      // M = 128, N = 32, A MN-major, B K-major, fp16 x fp16 -> fp32
+      constexpr uint32_t idesc = (1u << 4) | (1u << 15) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      q_mbar_wait(&wbar, 0);
+      uint32_t hphase[2] = {0, 0};
+      long long c_wait = 0, c_issue = 0;
+      for (int s = 0; s < T; ++s) {
+        const int b = s & 1;
+        const long long c0 = q_clock();
+        if (s > 0) {
+          q_mbar_expect_tx(&hbar[b], (uint32_t)CS * 4096u);
+          q_mbar_wait(&hbar[b], hphase[b]);
+          hphase[b] ^= 1;
+        }
+        q_fence_after();
+        const long long c1 = q_clock();
+        c_wait += c1 - c0;
+        // descriptors differ from the k-step-0 ones only in the 14-bit start-address field (units of 16 bytes)
+        const uint64_t a_hi0 = q_desc(q_smem(sWhi), 8192, 1024, 2), a_lo0 = q_desc(q_smem(sWlo), 8192, 1024, 2);
+        const uint32_t bH = q_smem(sH + (size_t)b * 2 * HBYTES);
+        const uint64_t b_hi0 = q_desc(bH, 16, 512, 4), b_lo0 = q_desc(bH + HBYTES, 16, 512, 4);
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+          if (ks < KSTEPS) {
+            const uint64_t a_off = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 128);     // 16 KB per k-box, 2 KB per k-step
+            const uint64_t b_off = (uint64_t)((ks >> 1) * 128 + (ks & 1) * 2);        // 2 KB per chunk, 32 B per k-step
+            const uint32_t tc = tmem_base + (QACC + (ks % QCROSS)) * 32;
+            q_mma_f16(tc, a_lo0 + a_off, b_hi0 + b_off, idesc, ks < QCROSS ? 0u : 1u);     // cross terms
+            q_mma_f16(tc, a_hi0 + a_off, b_lo0 + b_off, idesc, 1u);
+            q_mma_f16(tmem_base + ((ks >> 1) % QACC) * 32, a_hi0 + a_off, b_hi0 + b_off, idesc,
+                      (ks < 2 * QACC && (ks & 1) == 0) ? 0u : 1u);                         // main
+          }
+        }
+        q_commit(&accbar);
+        c_issue += q_clock() - c1;
+      }
+      if (dbg != nullptr && blockIdx.x == 0) { dbg[0] = (unsigned long long)c_wait; dbg[1] = (unsigned long long)c_issue; }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps: one TMEM lane (gate column) x 16 utterances per thread =====================
+    const int q4 = warp & 3, half = warp >> 2;         // TMEM lane quadrant, utterance half of this warp
+    const int m = q4 * 32 + lane;                      // local gate column = TMEM lane
+    const int ul = m >> 2, g = m & 3;                  // local unit, gate
+    const int ug = rank * QU + ul;
+    const bool u_ok = ug < H;
+    const int gcol = rank * 128 + m;                   // global gate column (4 ug + g)
+    const bool col_ok = gcol < H4;
+    const int j0 = half * QC;                          // first utterance (TMEM column) of this thread
+    const bool has_peep = peep != nullptr;
+    const float w_ci = (has_peep && u_ok) ? peep[ug] : 0.f;
+    const float w_cf = (has_peep && u_ok) ? peep[H + ug] : 0.f;
+    const float w_co = (has_peep && u_ok) ? peep[2 * H + ug] : 0.f;
+    // result scale: (main + cross 2^-11) 2^-(eW + eH)
+    const int e = -(__ldg(w_exp) + eh);
+    const int e1 = (e > 126 || e < -115) ? e / 2 : e, e2 = e - e1;
+    const float ms1 = __int_as_float((127 + e1) << 23), ms2 = __int_as_float((127 + e2) << 23);
+    // the 4 cells this thread owns: utterances j0 + 4 i + g of the tile, unit ug
+    float c_prev[4], h_prev[4];
+    unsigned long long mbits[4];                       // mask of the utterance, bit t
+    int n_own[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      c_prev[i] = u_ok ? cell_init[ug] : 0.f;
+      h_prev[i] = u_ok ? hid_init[ug] : 0.f;
+      n_own[i] = tile * QN + j0 + 4 * i + g;
+      mbits[i] = 0ull;
+      if (n_own[i] < N)
+        for (int t = 0; t < T; ++t)
+          if (mask[(size_t)n_own[i] * T + t]) mbits[i] |= 1ull << t;
+    }
+    // hoisted input projection of the current step, for the 16 utterances of this thread's gate column
+    float xv[QC];
+    auto fetch = [&](int t) {
+#pragma unroll
+      for (int j = 0; j < QC; ++j) {
+        const int n = tile * QN + j0 + j;
+        xv[j] = (col_ok && n < N) ? __ldg(xw + ((size_t)n * T + t) * H4 + gcol) : 0.f;
+      }
+    };
+    fetch(backwards ? T - 1 : 0);
+    long long e_wait = 0, e_ld = 0, e_math = 0, e_push = 0;
+    const int nacc = (KSTEPS / 2) < QACC ? (KSTEPS / 2) : QACC;
+    for (int s = 0; s < T; ++s) {
+      const int t = backwards ? (T - 1 - s) : s;
+      const long long k0 = q_clock();
+      q_mbar_wait(&accbar, (uint32_t)(s & 1));
+      q_fence_after();
+      const long long k1 = q_clock();
+      e_wait += k1 - k0;
+      float a[QC];
+      {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)j0;
+        float c0[QC], c1[QC], c2[QC], c3[QC];
+        q_tmem_ld16(taddr + QACC * 32, c0);              // cross terms (smallest) ...
+        q_tmem_ld16(taddr + (QACC + 1) * 32, c1);
+        q_tmem_ld16(taddr, c2);                          // ... and the first two main accumulators
+        q_tmem_ld16(taddr + 32, c3);
+        q_tmem_wait();
+#pragma unroll
+        for (int j = 0; j < QC; ++j) {
+          const float cr = KSTEPS >= QCROSS ? c0[j] + c1[j] : c0[j];
+          a[j] = fmaf(cr, 1.0f / 2048.0f, c2[j]);
+          if (nacc > 1) a[j] += c3[j];
+        }
+#pragma unroll 1
+        for (int q = 2; q + 1 < nacc; q += 2) {          // two more accumulators per TMEM round trip
+          q_tmem_ld16(taddr + q * 32, c0);
+          q_tmem_ld16(taddr + (q + 1) * 32, c1);
+          q_tmem_wait();
+#pragma unroll
+          for (int j = 0; j < QC; ++j) a[j] += c0[j] + c1[j];
+        }
+        if ((nacc & 1) && nacc > 2) {
+          q_tmem_ld16(taddr + (nacc - 1) * 32, c0);
+          q_tmem_wait();
+#pragma unroll
+          for (int j = 0; j < QC; ++j) a[j] += c0[j];
+        }
+      }
+      q_fence_before();
+      const long long k2 = q_clock();
+      e_ld += k2 - k1;
+#pragma unroll
+      for (int j = 0; j < QC; ++j) a[j] = a[j] * ms1 * ms2 + xv[j];
+      if (s + 1 < T) fetch(backwards ? (T - 2 - s) : (s + 1));
+      // 4x4 transpose inside each group of 4 lanes (the 4 gates of a unit): afterwards a[4i + q] = gate q of utterance j0 + 4i + g
+      const bool b0 = (g & 1) != 0, b1 = (g & 2) != 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float x0 = a[4 * i], x1 = a[4 * i + 1], x2 = a[4 * i + 2], x3 = a[4 * i + 3];
+        float r0 = __shfl_xor_sync(0xffffffffu, b0 ? x0 : x1, 1);
+        float r1 = __shfl_xor_sync(0xffffffffu, b0 ? x2 : x3, 1);
+        if (b0) { x0 = r0; x2 = r1; } else { x1 = r0; x3 = r1; }
+        r0 = __shfl_xor_sync(0xffffffffu, b1 ? x0 : x2, 2);
+        r1 = __shfl_xor_sync(0xffffffffu, b1 ? x1 : x3, 2);
+        if (b1) { x0 = r0; x1 = r1; } else { x2 = r0; x3 = r1; }
+        a[4 * i] = x0; a[4 * i + 1] = x1; a[4 * i + 2] = x2; a[4 * i + 3] = x3;
+      }
+      uint8_t* stg = sStage + (size_t)(s & 1) * 4096;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool mk = (mbits[i] >> t) & 1ull;
+        const CellF r = q_cell(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3], c_prev[i], h_prev[i], mk, has_peep, w_ci,
+                               w_cf, w_co);
+        if (u_ok && n_own[i] < N) {
+          const size_t row = (size_t)n_own[i] * T + t;
+          out[row * ldh + ug] = r.h;
+          if (gates) *reinterpret_cast<float4*>(gates + row * H4 + 4 * ug) = make_float4(r.i, r.f, r.cin, r.o);
+          if (cell) cell[row * H + ug] = r.c;
+          if (hprev) hprev[row * ldh + ug] = h_prev[i];
+        }
+        c_prev[i] = r.c;
+        h_prev[i] = r.h;
+        // h_{t+1} of (utterance j0 + 4i + g, unit ul) into the staging chunk, fp16 hi/lo, SWIZZLE_64B K-major layout
+        const float xs = (u_ok ? r.h : 0.f) * hs;
+        const __half hi = __float2half_rn(xs);
+        const __half lo = __float2half_rn((xs - __half2float(hi)) * 2048.0f);
+        const uint32_t off = q_sw64(j0 + 4 * i + g, ul);
+        *reinterpret_cast<__half*>(stg + off) = hi;
+        *reinterpret_cast<__half*>(stg + 2048 + off) = lo;
+      }
+      const long long k3 = q_clock();
+      e_math += k3 - k2;
+      if (s + 1 < T) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // push my chunk of h_{t+1} into the next-step operand tile of every CTA of the cluster (my own included)
+        if (tid < CS) {
+          const int nb = (s + 1) & 1;
+          const uint32_t dst_hi = q_smem(sH + (size_t)nb * 2 * HBYTES + (size_t)rank * 2048);
+          const uint32_t bar = q_mapa(q_smem(&hbar[nb]), (uint32_t)tid);
+          q_bulk_s2s(q_mapa(dst_hi, (uint32_t)tid), q_smem(stg), 2048, bar);
+          q_bulk_s2s(q_mapa(dst_hi + HBYTES, (uint32_t)tid), q_smem(stg + 2048), 2048, bar);
+        }
+      }
+      e_push += q_clock() - k3;
+    }
+    if (dbg != nullptr && blockIdx.x == 0 && tid == 0) {
+      dbg[2] = (unsigned long long)e_wait; dbg[3] = (unsigned long long)e_ld;
+      dbg[4] = (unsigned long long)e_math; dbg[5] = (unsigned long long)e_push;
+    }
+  }
+  q_fence_before();
+  q_cluster_sync();      // no CTA leaves while copies into / out of its shared memory may still be in flight
+  if (warp == 8) {
+    q_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)QTMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*QEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static QEncodeFn q_get_encode() {
+  static QEncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<QEncodeFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace ipavsr
+
+using namespace ipavsr;
+
+extern "C" {
+
+int ipavsr_lstm_fwd_f16_supported(int N, int T, int H, int ldw) {
+  (void)N;
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("IPAVSR_LSTM_TC");
+    off = (e && e[0] == '0') ? 1 : 0;
+  }
+  return (!off && H >= 8 && H <= 256 && T >= 1 && T <= 64 && ldw % 8 == 0 && ldw >= 4 * H) ? 1 : 0;
+}
+
+int ipavsr_lstm_fwd_f16(const float* xw, const uint16_t* whid_hi, const uint16_t* whid_lo, const int32_t* whid_exp,
+                        int ldw, const float* peep, const float* cell_init, const float* hid_init, const uint8_t* mask,
+                        float* out, float* gates, float* cell, float* hprev, int N, int T, int H, int ldh, int backwards,
+                        void* stream) {
+  IPAVSR_CHECK_ARG(xw && whid_hi && whid_lo && whid_exp && cell_init && hid_init && mask && out, "null pointer");
+  IPAVSR_CHECK_ARG(N >= 0 && T >= 1 && H >= 1 && ldh >= H, "bad sizes");
+  if (!ipavsr_lstm_fwd_f16_supported(N, T, H, ldw) ||
+      ((reinterpret_cast<uintptr_t>(whid_hi) | reinterpret_cast<uintptr_t>(whid_lo)) & 15) != 0) {
+    set_error("ipavsr_lstm_fwd_f16: needs 8 <= H <= 256, T <= 64, 16-byte aligned W_hid halves with ldw %% 8 == 0");
+    return IPAVSR_ERR_UNSUPPORTED;
+  }
+  if (N == 0) return IPAVSR_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  QEncodeFn enc = q_get_encode();
+  if (enc == nullptr) {
+    set_error("ipavsr_lstm_fwd_f16: cuTensorMapEncodeTiled is not available from the driver");
+    return IPAVSR_ERR_CUDA;
+  }
+  // W_hid split: fp16 [H rows (k)][4H gate columns], row stride ldw halves; box {64 columns, 64 k-rows}, 128B swizzle
+  CUtensorMap maps[2];
+  const uint16_t* base[2] = {whid_hi, whid_lo};
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)(4 * H), (cuuint64_t)H};
+    cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base[i]), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("ipavsr_lstm_fwd_f16: cuTensorMapEncodeTiled failed with %d", (int)r);
+      return IPAVSR_ERR_CUDA;
+    }
+  }
+  const int cs = (H + QU - 1) / QU;
+  const int kb = (cs * QU + 63) / 64;
+  const size_t smem = (size_t)2 * kb * 16384 + (size_t)4 * cs * 2048 + 2 * 4096 + 1024;
+  const int tiles = (N + QN - 1) / QN;
+  IPAVSR_CUDA(cudaFuncSetAttribute(lstm_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * cs);
+  cfg.blockDim = dim3(QTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  IPAVSR_CUDA(cudaLaunchKernelEx(&cfg, lstm_fwd_tc_kernel, maps[0], maps[1], xw, whid_exp, peep, cell_init, hid_init, mask,
+                                 out, gates, cell, hprev, N, T, H, ldh, backwards, g_lstm_dbg));
+  count_launch();
+  return IPAVSR_OK;
+}
+
+}  // extern "C"
+
+extern "C" int ipavsr_debug_lstm_timestamps(unsigned long long* buf) {
+  ipavsr::g_lstm_dbg = buf;
+  return IPAVSR_OK;
+}

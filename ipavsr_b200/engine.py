@@ -629,11 +629,21 @@ class Engine(object):
                     side, sh = self._fork()
                 else:
                     ws, side, sh = self._workspace(nbytes), None, st
-                _lib.call('ipavsr_lstm_fwd', xw.ptr, ar.mat((l, 'W_hid')).ptr, peep, ar.mat((l, 'cell_init')).ptr,
-                          ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
-                          gates.ptr if gates else None, cell.ptr if cell else None, hprev.ptr if hprev else None,
-                          N, T, H, out.ld, 1 if l.backwards else 0, self.lstm_impl, ws.data_ptr(),
-                          int(nbytes) if (self.lstm_impl != 0 or not self.concurrent_lstm) else 16, sh)
+                whid = ar.mat((l, 'W_hid'))
+                if (self.gemm_mode == 4 and self.lstm_impl == 0 and
+                        lib.ipavsr_lstm_fwd_f16_supported(N, T, H, whid.ld)):
+                    # tensor-core recurrence on the fp16 split of W_hid that the parameter arena already carries
+                    wh, wl, we = self._split16(whid)
+                    _lib.call('ipavsr_lstm_fwd_f16', xw.ptr, wh, wl, we, whid.ld, peep, ar.mat((l, 'cell_init')).ptr,
+                              ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
+                              gates.ptr if gates else None, cell.ptr if cell else None, hprev.ptr if hprev else None,
+                              N, T, H, out.ld, 1 if l.backwards else 0, sh)
+                else:
+                    _lib.call('ipavsr_lstm_fwd', xw.ptr, whid.ptr, peep, ar.mat((l, 'cell_init')).ptr,
+                              ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
+                              gates.ptr if gates else None, cell.ptr if cell else None, hprev.ptr if hprev else None,
+                              N, T, H, out.ld, 1 if l.backwards else 0, self.lstm_impl, ws.data_ptr(),
+                              int(nbytes) if (self.lstm_impl != 0 or not self.concurrent_lstm) else 16, sh)
                 if side is not None:
                     ev = torch.cuda.Event()
                     ev.record(side)

@@ -183,6 +183,83 @@ def test_lstm_fwd_bwd(impl, N, T, I, H, peep, backwards, scale):
         assert G.relerr(G.host(d_dpeep), gr['peep']) < tol, ('peep', G.relerr(G.host(d_dpeep), gr['peep']))
 
 
+@pytest.mark.parametrize('N,T,H,peep,backwards', [(26, 40, 250, True, False), (70, 40, 250, False, True), (5, 7, 40, True, True),
+                                                    (33, 3, 8, True, False), (512, 40, 250, True, False), (40, 64, 256, True, True),
+                                                    (9, 1, 100, False, False)])
+def test_lstm_fwd_tensor_core(N, T, H, peep, backwards):
+    """ipavsr_lstm_fwd_f16 (tcgen05 recurrence on the fp16 split of W_hid) == oracle, including the training saves."""
+    rng = np.random.default_rng(N + T + H)
+    lens = rng.integers(1, T + 1, size=N)
+    lens[0] = T
+    p, x, mask = _lstm_inputs(rng, N, T, 12, H, peep, lens)
+    p['hid_init'] = (p['hid_init'] * (4.0 if backwards else 1.0)).astype('float32')       # |hid_init| > 1 too
+    if H >= 100:
+        # N(0, 0.3) at H = 250 is an expanding recurrence (gain ~1.2 per step) that amplifies the ~2e-7 per-step error of
+        # the three-product tensor-core arithmetic (truncating TMEM accumulation) to ~1e-4 over 40 steps; the models use
+        # orthogonal recurrent weights (gain <= 0.25 per step).  Keep the recurrence non-expanding here.
+        p['W_hid'] = (p['W_hid'] * 0.25).astype('float32')
+    out_ref, cache = ops.lstm_fwd(x, mask, p, backwards, np.float64)
+    xw = (x.reshape(N * T, 12).astype(np.float64) @ p['W_in'].astype(np.float64) + p['b']).astype('float32')
+    ldh = (H + 7) // 8 * 8
+    ldw = (4 * H + 7) // 8 * 8
+    whid = np.zeros((H, ldw), 'float32')
+    whid[:, :4 * H] = G.interleave_gates(p['W_hid'], H)
+    d_xw, d_whid = G.dev(G.interleave_gates(xw, H)), G.dev(whid)
+    wh, wl = G.zeros((H, ldw), torch.float16), G.zeros((H, ldw), torch.float16)
+    sc = G.zeros((2,))
+    G.call('ipavsr_f16_split', d_whid.data_ptr(), ldw, H, 4 * H, wh.data_ptr(), wl.data_ptr(), ldw, sc.data_ptr(),
+           sc.data_ptr() + 4, 0, G.stream())
+    d_peep = G.dev(p['peep']) if peep else None
+    d_ci, d_hi, d_mask = G.dev(p['cell_init']), G.dev(p['hid_init']), G.dev(mask)
+    d_out, d_gates = G.zeros((N * T, ldh)), G.zeros((N * T, 4 * H))
+    d_cell, d_hprev = G.zeros((N * T, H)), G.zeros((N * T, ldh))
+    assert G.lib().ipavsr_lstm_fwd_f16_supported(N, T, H, ldw)
+    G.call('ipavsr_lstm_fwd_f16', d_xw.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4, ldw, G.ptr(d_peep),
+           d_ci.data_ptr(), d_hi.data_ptr(), d_mask.data_ptr(), d_out.data_ptr(), d_gates.data_ptr(), d_cell.data_ptr(),
+           d_hprev.data_ptr(), N, T, H, ldh, int(backwards), G.stream())
+    out = G.host(d_out)[:, :H].reshape(N, T, H)
+    tol = 2e-5
+    assert G.relerr(out, out_ref) < tol, G.relerr(out, out_ref)
+    # training saves agree with the FFMA kernel's
+    e_out, e_gates = G.zeros((N * T, ldh)), G.zeros((N * T, 4 * H))
+    e_cell, e_hprev = G.zeros((N * T, H)), G.zeros((N * T, ldh))
+    nbytes = G.lib().ipavsr_lstm_workspace_bytes(N, T, H)
+    ws = G.zeros(((nbytes + 3) // 4,))
+    d_w32 = G.dev(G.interleave_gates(p['W_hid'], H))
+    G.call('ipavsr_lstm_fwd', d_xw.data_ptr(), d_w32.data_ptr(), G.ptr(d_peep), d_ci.data_ptr(), d_hi.data_ptr(),
+           d_mask.data_ptr(), e_out.data_ptr(), e_gates.data_ptr(), e_cell.data_ptr(), e_hprev.data_ptr(), N, T, H, ldh,
+           int(backwards), 0, ws.data_ptr(), nbytes, G.stream())
+    for a, b, name in ((d_gates, e_gates, 'gates'), (d_cell, e_cell, 'cell'), (d_hprev, e_hprev, 'hprev'), (d_out, e_out, 'out')):
+        assert G.relerr(G.host(a), G.host(b)) < tol, name
+
+
+def test_lstm_fwd_tensor_core_orthogonal_weights():
+    """With the models' own initialisation (orthogonal W_hid, lasagne.init.Orthogonal) the tensor-core recurrence holds the
+    1e-5 gate of the FFMA kernel over T = 40."""
+    rng = np.random.default_rng(5)
+    N, T, H = 64, 40, 250
+    lens = rng.integers(12, T + 1, size=N)
+    p, x, mask = _lstm_inputs(rng, N, T, 150, H, True, lens)
+    for g in range(4):
+        q, _ = np.linalg.qr(rng.normal(size=(H, H)))
+        p['W_hid'][:, g * H:(g + 1) * H] = q.astype('float32')
+    p['W_in'] = (p['W_in'] / np.sqrt(150) / 0.3).astype('float32')
+    out_ref, _ = ops.lstm_fwd(x, mask, p, False, np.float64)
+    xw = (x.reshape(N * T, 150).astype(np.float64) @ p['W_in'].astype(np.float64) + p['b']).astype('float32')
+    ldh, ldw = 256, 1000
+    d_xw, d_whid = G.dev(G.interleave_gates(xw, H)), G.dev(G.interleave_gates(p['W_hid'], H))
+    wh, wl, sc = G.zeros((H, ldw), torch.float16), G.zeros((H, ldw), torch.float16), G.zeros((2,))
+    G.call('ipavsr_f16_split', d_whid.data_ptr(), ldw, H, 4 * H, wh.data_ptr(), wl.data_ptr(), ldw, sc.data_ptr(),
+           sc.data_ptr() + 4, 0, G.stream())
+    d_out = G.zeros((N * T, ldh))
+    d_peep, d_ci, d_hi, d_mask = G.dev(p['peep']), G.dev(p['cell_init']), G.dev(p['hid_init']), G.dev(mask)
+    G.call('ipavsr_lstm_fwd_f16', d_xw.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4, ldw,
+           d_peep.data_ptr(), d_ci.data_ptr(), d_hi.data_ptr(), d_mask.data_ptr(), d_out.data_ptr(), None, None, None,
+           N, T, H, ldh, 0, G.stream())
+    err = G.relerr(G.host(d_out)[:, :H].reshape(N, T, H), out_ref)
+    assert err < 1e-5, err
+
+
 def test_lstm_impls_agree_large():
     """persistent cluster kernel == step-wise form at a batch that spans several cluster tiles."""
     rng = np.random.default_rng(77)

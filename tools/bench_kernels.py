@@ -163,6 +163,13 @@ if 'lstm' in only:
         ms = timeit(lambda: _lib.call('ipavsr_lstm_fwd', xw.data_ptr(), whid.data_ptr(), peep.data_ptr(), ci.data_ptr(), hi.data_ptr(), mask.data_ptr(),
                                       out.data_ptr(), None, None, None, N, T, H, ldh, 0, 0, ws.data_ptr(), nbytes, st()), reps=5)
         report('lstm_fwd N=%d H=%d impl=0 (inference)' % (N, H), ms, flops=2.0 * N * T * H * 4 * H, extra='  %.2f us/step' % (ms * 1e3 / T))
+        if lib.ipavsr_lstm_fwd_f16_supported(N, T, H, 4 * H):
+            wh, wl = torch.empty(H, 4 * H, dtype=torch.float16, device='cuda'), torch.empty(H, 4 * H, dtype=torch.float16, device='cuda')
+            sc = torch.zeros(2, device='cuda')
+            _lib.call('ipavsr_f16_split', whid.data_ptr(), 4 * H, H, 4 * H, wh.data_ptr(), wl.data_ptr(), 4 * H, sc.data_ptr(), sc.data_ptr() + 4, 0, st())
+            ms = timeit(lambda: _lib.call('ipavsr_lstm_fwd_f16', xw.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4, 4 * H, peep.data_ptr(), ci.data_ptr(),
+                                          hi.data_ptr(), mask.data_ptr(), out.data_ptr(), gates.data_ptr(), cell.data_ptr(), hprev.data_ptr(), N, T, H, ldh, 0, st()), reps=5)
+            report('lstm_fwd_f16 N=%d H=%d tcgen05 (train saves)' % (N, H), ms, flops=2.0 * N * T * H * 4 * H, extra='  %.2f us/step' % (ms * 1e3 / T))
         del xw, out, hprev, gates, cell, dout, dg, ws
 if 'opt' in only:
     n = 24 * 1024 * 1024
