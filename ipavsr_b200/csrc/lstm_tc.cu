@@ -26,6 +26,9 @@
 
 namespace ipavsr {
 
+int gemm_simt(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+              float* C, int ldc, const float* bias, int act, int accumulate, cudaStream_t st);
+
 namespace {
 
 constexpr int QN = 32;            // utterances per cluster tile (MMA N)
@@ -461,6 +464,285 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
   }
 }
 
+// =========================================================================================================
+// Backward (BPTT) on the tensor cores.  CTA r owns units U_r = [32r, 32r+32) and their gate columns J_r.  Per processed
+// step (in reverse order):
+//   1. 256 threads run the cell backward for the CTA's 32 units x 32 utterances (4 cells each): the recurrent gradient
+//      dh_next is the sum of the CS partial blocks that landed in the inbox, dg (clipped) goes to global memory and,
+//      as fp16 hi/lo (static scale: |dg| <= clip), into a K-major SWIZZLE_128B operand tile [32 utterances x 128 j];
+//   2. one thread issues  D[k, n] = sum_{j in J_r} W_hid[k, j] dg[n, j]  for ALL k: 2 row blocks x 8 k-steps x 3 products,
+//      A = the CTA's column slice of W_hid (K-major, resident, TMA-loaded from the arena split);
+//   3. every thread reads its k row (32 utterances) from TMEM and stores it into the inbox of the CTA that owns unit k
+//      (distributed shared memory, 8 x 16-byte stores), i.e. a reduce-scatter of the partial products;
+//   4. one cluster barrier makes the inboxes visible.
+// =========================================================================================================
+struct CellB {
+  float dgi, dgf, dgc, dgo, dc_prev, dh_pass, pci, pcf, pco;
+};
+__device__ __forceinline__ CellB q_cell_bwd(float dh, float dc, float i, float f, float cin, float o, float c, float c_prev,
+                                            bool m, bool has_peep, float w_ci, float w_cf, float w_co, float clip) {
+  CellB g;
+  if (!m) {
+    g.dgi = g.dgf = g.dgc = g.dgo = 0.f;
+    g.dc_prev = dc;
+    g.dh_pass = dh;
+    g.pci = g.pcf = g.pco = 0.f;
+    return g;
+  }
+  const float tc = q_tanh(c);
+  float dgo = dh * tc * o * (1.f - o);
+  float dcu = dc + dh * o * (1.f - tc * tc);
+  if (has_peep) dcu = fmaf(dgo, w_co, dcu);
+  float dgi = dcu * cin * i * (1.f - i);
+  float dgf = dcu * c_prev * f * (1.f - f);
+  float dgc = dcu * i * (1.f - cin * cin);
+  g.dc_prev = dcu * f;
+  if (has_peep) g.dc_prev += dgi * w_ci + dgf * w_cf;
+  g.pci = dgi * c_prev;
+  g.pcf = dgf * c_prev;
+  g.pco = dgo * c;
+  if (clip > 0.f) {
+    dgi = fminf(fmaxf(dgi, -clip), clip);
+    dgf = fminf(fmaxf(dgf, -clip), clip);
+    dgc = fminf(fmaxf(dgc, -clip), clip);
+    dgo = fminf(fmaxf(dgo, -clip), clip);
+  }
+  g.dgi = dgi; g.dgf = dgf; g.dgc = dgc; g.dgo = dgo;
+  g.dh_pass = 0.f;
+  return g;
+}
+
+constexpr int BACC = 4;           // main accumulators per row block (2 k-steps each at K = 128)
+constexpr int BCOLS = (BACC + QCROSS) * 32;      // TMEM columns per row block
+
+__global__ void __launch_bounds__(QTHREADS, 1)
+lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
+                   const float* __restrict__ dout, const int32_t* __restrict__ w_exp, const float* __restrict__ peep,
+                   const float* __restrict__ cell_init, const uint8_t* __restrict__ mask, const float* __restrict__ gates,
+                   const float* __restrict__ cell, float* __restrict__ dgates, float* __restrict__ dpeep,
+                   float* __restrict__ dc_fin, float* __restrict__ dh_fin, int N, int T, int H, int ldh, int backwards,
+                   float clip, int eg) {
+  const int CS = (int)q_cluster_size();
+  const int rank = (int)q_cluster_rank();
+  const int tile = blockIdx.x / CS;
+  const int H4 = 4 * H;
+  const int MB = (CS * QU + 127) / 128;                // 128-row blocks of the k dimension (1 or 2)
+
+  extern __shared__ uint8_t q_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(q_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sWhi = smem;                                // [MB][2 j-chunks][128 rows x 128 B]
+  uint8_t* sWlo = sWhi + (size_t)MB * 32768;
+  uint8_t* sB = sWlo + (size_t)MB * 32768;             // dg operand: [hi | lo][2 j-chunks][32 rows x 128 B]
+  float* inbox = reinterpret_cast<float*>(sB + 16384); // [2 parities][CS sources][32 units][32 utterances]
+  __shared__ __align__(8) uint64_t accbar, wbar, bready;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    q_mbar_init(&accbar, 1);
+    q_mbar_init(&wbar, 1);
+    q_mbar_init(&bready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(q_smem(&tmem_base_smem)),
+                 "r"((uint32_t)QTMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  q_fence_before();
+  __syncthreads();
+  q_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (tid == 0) {
+    // W_hid[:, J_r]: all k rows x the CTA's 128 gate columns, K-major (j contiguous), from the fp16 split of the arena
+    q_mbar_expect_tx(&wbar, (uint32_t)MB * 65536u);
+    for (int mb = 0; mb < MB; ++mb)
+      for (int jc = 0; jc < 2; ++jc) {
+        q_tma_load_2d(sWhi + (size_t)(mb * 2 + jc) * 16384, &mapWhi, &wbar, rank * 128 + jc * 64, mb * 128);
+        q_tma_load_2d(sWlo + (size_t)(mb * 2 + jc) * 16384, &mapWlo, &wbar, rank * 128 + jc * 64, mb * 128);
+      }
+  }
+  q_cluster_sync();
+
+  if (warp == 8) {
+    // ===================== control warp =====================
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // K-major A and B
+    if (lane == 0) q_mbar_wait(&wbar, 0);
+    for (int s = T - 1; s >= 1; --s) {
+      if (lane == 0) {
+        q_mbar_wait(&bready, (uint32_t)((T - 1 - s) & 1));
+        q_fence_after();
+        const uint64_t b_hi0 = q_desc(q_smem(sB), 16, 1024, 2), b_lo0 = q_desc(q_smem(sB + 8192), 16, 1024, 2);
+        for (int mb = 0; mb < MB; ++mb) {
+          const uint64_t a_hi0 = q_desc(q_smem(sWhi + (size_t)mb * 32768), 16, 1024, 2);
+          const uint64_t a_lo0 = q_desc(q_smem(sWlo + (size_t)mb * 32768), 16, 1024, 2);
+          const uint32_t tb = tmem_base + (uint32_t)(mb * BCOLS);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a_off = (uint64_t)((ks >> 2) * 1024 + (ks & 3) * 2);      // 16 KB per j-chunk, 32 B per k-step
+            const uint64_t b_off = (uint64_t)((ks >> 2) * 256 + (ks & 3) * 2);       // 4 KB per j-chunk
+            const uint32_t tc = tb + (BACC + (ks % QCROSS)) * 32;
+            q_mma_f16(tc, a_lo0 + a_off, b_hi0 + b_off, idesc, ks < QCROSS ? 0u : 1u);
+            q_mma_f16(tc, a_hi0 + a_off, b_lo0 + b_off, idesc, 1u);
+            q_mma_f16(tb + (ks >> 1) * 32, a_hi0 + a_off, b_hi0 + b_off, idesc, (ks & 1) ? 1u : 0u);
+          }
+        }
+        q_commit(&accbar);
+      }
+      __syncwarp();
+      q_cluster_sync();
+    }
+  } else {
+    // ===================== 256 worker threads =====================
+    // cell mapping: unit ul = tid >> 3, utterances n = 4 (tid & 7) + i (one float4 of an inbox row)
+    const int ul = tid >> 3, nq = tid & 7;
+    const int ug = rank * QU + ul;
+    const bool u_ok = ug < H;
+    // TMEM mapping: row block mbk = warp >> 2, lane quadrant warp & 3 -> k row; its owner CTA is the same for the warp
+    const int mbk = warp >> 2;
+    const int krow = mbk * 128 + (warp & 3) * 32 + lane;
+    const int owner = krow >> 5;
+    const bool has_peep = peep != nullptr;
+    const float w_ci = (has_peep && u_ok) ? peep[ug] : 0.f;
+    const float w_cf = (has_peep && u_ok) ? peep[H + ug] : 0.f;
+    const float w_co = (has_peep && u_ok) ? peep[2 * H + ug] : 0.f;
+    const int e = -(__ldg(w_exp) + eg);
+    const int e1 = (e > 126 || e < -115) ? e / 2 : e, e2 = e - e1;
+    const float ms1 = __int_as_float((127 + e1) << 23), ms2 = __int_as_float((127 + e2) << 23);
+    const float gs = __int_as_float((127 + eg) << 23);          // 2^eG: scale of the dg operand
+    int ng[4];
+    bool n_ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ng[i] = tile * QN + 4 * nq + i;
+      n_ok[i] = ng[i] < N;
+    }
+    float dh_next[4] = {0.f, 0.f, 0.f, 0.f}, dc_next[4] = {0.f, 0.f, 0.f, 0.f}, dh_pass[4] = {0.f, 0.f, 0.f, 0.f};
+    float pci = 0.f, pcf = 0.f, pco = 0.f;
+    float pf_dout[4], pf_c[4], pf_cp[4];
+    float4 pf_g[4];
+    bool pf_m[4];
+    auto fetch = [&](int s) {
+      const int t = backwards ? (T - 1 - s) : s;
+      const int t_prev = (s == 0) ? -1 : (backwards ? t + 1 : t - 1);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pf_dout[i] = pf_c[i] = pf_cp[i] = 0.f;
+        pf_g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pf_m[i] = false;
+        if (n_ok[i] && u_ok) {
+          const size_t row = (size_t)ng[i] * T + t;
+          pf_dout[i] = __ldg(dout + row * ldh + ug);
+          pf_g[i] = __ldg(reinterpret_cast<const float4*>(gates + row * H4 + 4 * ug));
+          pf_c[i] = __ldg(cell + row * H + ug);
+          pf_cp[i] = t_prev < 0 ? cell_init[ug] : __ldg(cell + ((size_t)ng[i] * T + t_prev) * H + ug);
+          pf_m[i] = mask[row] != 0;
+        }
+      }
+    };
+    fetch(T - 1);
+    int par = 0;
+    for (int s = T - 1; s >= 0; --s) {
+      const int t = backwards ? (T - 1 - s) : s;
+      // ---- 1. cell backward for my 4 cells; dg -> global (fp32) and -> the fp16 operand tile ----
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+        dh_pass[i] = 0.f;
+        if (n_ok[i] && u_ok) {
+          const size_t row = (size_t)ng[i] * T + t;
+          const CellB g = q_cell_bwd(pf_dout[i] + dh_next[i], dc_next[i], pf_g[i].x, pf_g[i].y, pf_g[i].z, pf_g[i].w,
+                                     pf_c[i], pf_cp[i], pf_m[i], has_peep, w_ci, w_cf, w_co, clip);
+          dg = make_float4(g.dgi, g.dgf, g.dgc, g.dgo);
+          dc_next[i] = g.dc_prev;
+          dh_pass[i] = g.dh_pass;
+          pci += g.pci; pcf += g.pcf; pco += g.pco;
+          *reinterpret_cast<float4*>(dgates + row * H4 + 4 * ug) = dg;
+        }
+        // operand tile: row n = 4 nq + i, columns j = 4 ul .. 4 ul + 3 (8 bytes), 128-byte rows, 128B swizzle
+        const float v[4] = {dg.x * gs, dg.y * gs, dg.z * gs, dg.w * gs};
+        __half h[4], l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          h[q] = __float2half_rn(v[q]);
+          l[q] = __float2half_rn((v[q] - __half2float(h[q])) * 2048.0f);
+        }
+        const int n = 4 * nq + i;
+        const uint32_t off = (uint32_t)(ul >> 4) * 4096u + (uint32_t)n * 128u +
+                             (uint32_t)((((ul & 15) >> 1) ^ (n & 7)) << 4) + (uint32_t)(ul & 1) * 8u;
+        *reinterpret_cast<uint2*>(sB + off) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(sB + 8192 + off) = *reinterpret_cast<const uint2*>(l);
+      }
+      if (s == 0) break;   // the recurrent gradient of the first processed step goes to hid_init (host side)
+      fetch(s - 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(q_smem(&bready)) : "memory");
+      // ---- 2./3. my k row of the partial product -> the owner's inbox ----
+      q_mbar_wait(&accbar, (uint32_t)((T - 1 - s) & 1));
+      q_fence_after();
+      if (mbk < MB) {
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mbk * BCOLS);
+        if (owner < CS) {
+          float* box = inbox + (((size_t)par * CS + rank) * QU + lane) * QN;      // same offset in every CTA
+          const uint32_t remote = q_mapa(q_smem(box), (uint32_t)owner);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float a[QC], c0[QC], c1[QC], c2[QC], c3[QC], c4[QC];
+            q_tmem_ld16(taddr + BACC * 32 + hf * QC, c0);
+            q_tmem_ld16(taddr + (BACC + 1) * 32 + hf * QC, c1);
+            q_tmem_ld16(taddr + hf * QC, a);
+            q_tmem_ld16(taddr + 32 + hf * QC, c2);
+            q_tmem_ld16(taddr + 64 + hf * QC, c3);
+            q_tmem_ld16(taddr + 96 + hf * QC, c4);
+            q_tmem_wait();
+#pragma unroll
+            for (int j = 0; j < QC; ++j)
+              a[j] = (fmaf(c0[j] + c1[j], 1.0f / 2048.0f, a[j]) + c2[j] + (c3[j] + c4[j])) * ms1 * ms2;
+#pragma unroll
+            for (int j = 0; j < QC; j += 4)
+              asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(hf * QC + j) * 4u),
+                           "f"(a[j]), "f"(a[j + 1]), "f"(a[j + 2]), "f"(a[j + 3])
+                           : "memory");
+          }
+        }
+      }
+      q_fence_before();
+      // ---- 4. the inboxes of this step are complete ----
+      q_cluster_sync();
+      // ---- sum the CS partial blocks for my (unit, 4 utterances) ----
+      {
+        float4 acc = make_float4(dh_pass[0], dh_pass[1], dh_pass[2], dh_pass[3]);
+        for (int src = 0; src < CS; ++src) {
+          const float4 v = *reinterpret_cast<const float4*>(inbox + (((size_t)par * CS + src) * QU + ul) * QN + 4 * nq);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        dh_next[0] = acc.x; dh_next[1] = acc.y; dh_next[2] = acc.z; dh_next[3] = acc.w;
+      }
+      par ^= 1;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n_ok[i] && u_ok) {
+        dc_fin[(size_t)ng[i] * H + ug] = dc_next[i];
+        dh_fin[(size_t)ng[i] * H + ug] = dh_pass[i];
+      }
+    if (has_peep && u_ok) {
+      atomicAdd(dpeep + ug, pci);
+      atomicAdd(dpeep + H + ug, pcf);
+      atomicAdd(dpeep + 2 * H + ug, pco);
+    }
+  }
+  q_fence_before();
+  q_cluster_sync();
+  if (warp == 8) {
+    q_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)QTMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*QEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -548,6 +830,92 @@ int ipavsr_lstm_fwd_f16(const float* xw, const uint16_t* whid_hi, const uint16_t
                                  out, gates, cell, hprev, N, T, H, ldh, backwards, g_lstm_dbg));
   count_launch();
   return IPAVSR_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int ipavsr_lstm_bwd_f16_supported(int N, int T, int H, int ldw, float clip) {
+  return (ipavsr_lstm_fwd_f16_supported(N, T, H, ldw) && clip > 0.f && clip < 16384.f) ? 1 : 0;
+}
+
+int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* whid_hi, const uint16_t* whid_lo,
+                        const int32_t* whid_exp, int ldw, const float* peep, const float* cell_init, const uint8_t* mask,
+                        const float* gates, const float* cell, float* dgates, float* dpeep, float* dcell_init,
+                        float* dhid_init, int N, int T, int H, int ldh, int backwards, float clip, int accumulate,
+                        void* workspace, uint64_t workspace_bytes, void* stream) {
+  IPAVSR_CHECK_ARG(dout && w_hid && whid_hi && whid_lo && whid_exp && cell_init && mask && gates && cell && dgates &&
+                       dcell_init && dhid_init,
+                   "null pointer");
+  IPAVSR_CHECK_ARG((peep == nullptr) == (dpeep == nullptr), "peep and dpeep go together");
+  IPAVSR_CHECK_ARG(N >= 0 && T >= 1 && H >= 1 && ldh >= H, "bad sizes");
+  IPAVSR_CHECK_ARG(workspace && workspace_bytes >= (uint64_t)2 * N * H * sizeof(float), "workspace too small (2*N*H floats)");
+  if (!ipavsr_lstm_bwd_f16_supported(N, T, H, ldw, clip) ||
+      ((reinterpret_cast<uintptr_t>(whid_hi) | reinterpret_cast<uintptr_t>(whid_lo)) & 15) != 0) {
+    set_error("ipavsr_lstm_bwd_f16: needs 8 <= H <= 256, T <= 64, clip > 0, 16-byte aligned W_hid halves, ldw %% 8 == 0");
+    return IPAVSR_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!accumulate) {
+    IPAVSR_CUDA(cudaMemsetAsync(dcell_init, 0, sizeof(float) * H, st));
+    IPAVSR_CUDA(cudaMemsetAsync(dhid_init, 0, sizeof(float) * H, st));
+    if (dpeep) IPAVSR_CUDA(cudaMemsetAsync(dpeep, 0, sizeof(float) * 3 * H, st));
+  }
+  if (N == 0) return IPAVSR_OK;
+  QEncodeFn enc = q_get_encode();
+  if (enc == nullptr) {
+    set_error("ipavsr_lstm_bwd_f16: cuTensorMapEncodeTiled is not available from the driver");
+    return IPAVSR_ERR_CUDA;
+  }
+  // W_hid split, K-major A operand: box {64 gate columns (128 bytes), 128 k-rows}
+  CUtensorMap maps[2];
+  const uint16_t* base[2] = {whid_hi, whid_lo};
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)(4 * H), (cuuint64_t)H};
+    cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base[i]), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("ipavsr_lstm_bwd_f16: cuTensorMapEncodeTiled failed with %d", (int)r);
+      return IPAVSR_ERR_CUDA;
+    }
+  }
+  float* dc_fin = reinterpret_cast<float*>(workspace);
+  float* dh_fin = dc_fin + (size_t)N * H;
+  const int cs = (H + QU - 1) / QU;
+  const int mb = (cs * QU + 127) / 128;
+  const size_t smem = (size_t)2 * mb * 32768 + 16384 + (size_t)2 * cs * QU * QN * sizeof(float) + 1024;
+  const int tiles = (N + QN - 1) / QN;
+  // |dg| <= clip: static scale 2^eg with clip * 2^eg < 2^15
+  const int eg = 14 - (ilogbf(clip) + 1);
+  IPAVSR_CUDA(cudaFuncSetAttribute(lstm_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles * cs);
+  cfg.blockDim = dim3(QTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  IPAVSR_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel, maps[0], maps[1], dout, whid_exp, peep, cell_init, mask, gates,
+                                 cell, dgates, dpeep, dc_fin, dh_fin, N, T, H, ldh, backwards, clip, eg));
+  count_launch();
+  // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step
+  const int t_first = backwards ? T - 1 : 0;
+  int rc = gemm_simt(0, 1, N, H, 4 * H, dgates + (size_t)t_first * 4 * H, T * 4 * H, w_hid, 4 * H, dh_fin, H, nullptr,
+                     IPAVSR_ACT_LINEAR, 1, st);
+  if (rc) return rc;
+  rc = ipavsr_colsum(dh_fin, H, dhid_init, N, H, 1, stream);
+  if (rc) return rc;
+  return ipavsr_colsum(dc_fin, H, dcell_init, N, H, 1, stream);
 }
 
 }  // extern "C"

@@ -88,7 +88,7 @@ class ParamArena(object):
             elif isinstance(l, L.LSTMLayer):
                 H, I = l.num_units, l.num_inputs
                 add((l, 'W_in'), I, 4 * H)
-                add((l, 'W_hid'), H, 4 * H)
+                add((l, 'W_hid'), H, 4 * H, pad_ld=False)      # the recurrence kernels take a dense (H, 4H) matrix
                 add((l, 'b'), 1, 4 * H)
                 for g, name in enumerate(GATES):
                     self.bind[getattr(l, 'W_in_to_' + name)] = ((l, 'W_in'), ('gate', g))
@@ -892,10 +892,19 @@ class Engine(object):
         else:
             ws = self._workspace(nbytes)
         clip = l.grad_clipping if l.grad_clipping else 0.0
-        _lib.call('ipavsr_lstm_bwd', dout.ptr, ar.mat((l, 'W_hid')).ptr, peep, ar.mat((l, 'cell_init')).ptr,
-                  mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,
-                  G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
-                  self.lstm_impl, ws.data_ptr(), int(nbytes), stream_handle)
+        whid = ar.mat((l, 'W_hid'))
+        if (self.gemm_mode == 4 and self.lstm_impl == 0 and
+                lib.ipavsr_lstm_bwd_f16_supported(N, T, H, whid.ld, float(clip))):
+            wh, wl, we = self._split16(whid)
+            _lib.call('ipavsr_lstm_bwd_f16', dout.ptr, whid.ptr, wh, wl, we, whid.ld, peep, ar.mat((l, 'cell_init')).ptr,
+                      mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,
+                      G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
+                      ws.data_ptr(), int(nbytes), stream_handle)
+        else:
+            _lib.call('ipavsr_lstm_bwd', dout.ptr, whid.ptr, peep, ar.mat((l, 'cell_init')).ptr,
+                      mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,
+                      G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
+                      self.lstm_impl, ws.data_ptr(), int(nbytes), stream_handle)
         return dG
 
     def _proj_bwd(self, run, in_layer, xsegs, dZ, W, dW):

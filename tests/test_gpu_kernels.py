@@ -233,6 +233,65 @@ def test_lstm_fwd_tensor_core(N, T, H, peep, backwards):
         assert G.relerr(G.host(a), G.host(b)) < tol, name
 
 
+@pytest.mark.parametrize('N,T,H,peep,backwards,scale', [(26, 40, 250, True, False, 1.0), (70, 40, 250, False, True, 30.0),
+                                                          (5, 7, 40, True, True, 1.0), (33, 3, 8, True, False, 1.0),
+                                                          (200, 12, 256, True, True, 1.0), (9, 1, 100, False, False, 1.0)])
+def test_lstm_bwd_tensor_core(N, T, H, peep, backwards, scale):
+    """ipavsr_lstm_bwd_f16 (tcgen05 BPTT) == the FFMA kernel and the oracle on the same saved tensors."""
+    rng = np.random.default_rng(N + 2 * T + H)
+    lens = rng.integers(1, T + 1, size=N)
+    lens[0] = T
+    I = 12
+    p, x, mask = _lstm_inputs(rng, N, T, I, H, peep, lens)
+    if H >= 100:
+        p['W_hid'] = (p['W_hid'] * 0.25).astype('float32')
+    dout = (rng.normal(size=(N, T, H)) * scale).astype('float32')
+    out_ref, cache = ops.lstm_fwd(x, mask, p, backwards, np.float64)
+    dx_ref, gr = ops.lstm_bwd(dout, cache, 5.0, np.float64)
+    xw = (x.reshape(N * T, I).astype(np.float64) @ p['W_in'].astype(np.float64) + p['b']).astype('float32')
+    ldh, ldw = (H + 7) // 8 * 8, 4 * H
+    d_xw = G.dev(G.interleave_gates(xw, H))
+    d_whid = G.dev(G.interleave_gates(p['W_hid'], H))
+    wh, wl, sc = G.zeros((H, ldw), torch.float16), G.zeros((H, ldw), torch.float16), G.zeros((2,))
+    G.call('ipavsr_f16_split', d_whid.data_ptr(), ldw, H, 4 * H, wh.data_ptr(), wl.data_ptr(), ldw, sc.data_ptr(),
+           sc.data_ptr() + 4, 0, G.stream())
+    d_peep = G.dev(p['peep']) if peep else None
+    d_ci, d_hi, d_mask = G.dev(p['cell_init']), G.dev(p['hid_init']), G.dev(mask)
+    d_out, d_gates = G.zeros((N * T, ldh)), G.zeros((N * T, 4 * H))
+    d_cell, d_hprev = G.zeros((N * T, H)), G.zeros((N * T, ldh))
+    nbytes = G.lib().ipavsr_lstm_workspace_bytes(N, T, H)
+    ws = G.zeros(((nbytes + 3) // 4,))
+    G.call('ipavsr_lstm_fwd', d_xw.data_ptr(), d_whid.data_ptr(), G.ptr(d_peep), d_ci.data_ptr(), d_hi.data_ptr(),
+           d_mask.data_ptr(), d_out.data_ptr(), d_gates.data_ptr(), d_cell.data_ptr(), d_hprev.data_ptr(), N, T, H, ldh,
+           int(backwards), 0, ws.data_ptr(), nbytes, G.stream())
+    dop = np.zeros((N * T, ldh), 'float32')
+    dop[:, :H] = dout.reshape(N * T, H)
+    d_dout = G.dev(dop)
+    res = []
+    for tc in (True, False):
+        d_dg, d_dpeep = G.zeros((N * T, 4 * H)), (G.zeros((3, H)) if peep else None)
+        d_dci, d_dhi = G.zeros((H,)), G.zeros((H,))
+        if tc:
+            assert G.lib().ipavsr_lstm_bwd_f16_supported(N, T, H, ldw, 5.0)
+            G.call('ipavsr_lstm_bwd_f16', d_dout.data_ptr(), d_whid.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4,
+                   ldw, G.ptr(d_peep), d_ci.data_ptr(), d_mask.data_ptr(), d_gates.data_ptr(), d_cell.data_ptr(),
+                   d_dg.data_ptr(), G.ptr(d_dpeep), d_dci.data_ptr(), d_dhi.data_ptr(), N, T, H, ldh, int(backwards), 5.0, 0,
+                   ws.data_ptr(), nbytes, G.stream())
+        else:
+            G.call('ipavsr_lstm_bwd', d_dout.data_ptr(), d_whid.data_ptr(), G.ptr(d_peep), d_ci.data_ptr(), d_mask.data_ptr(),
+                   d_gates.data_ptr(), d_cell.data_ptr(), d_dg.data_ptr(), G.ptr(d_dpeep), d_dci.data_ptr(), d_dhi.data_ptr(),
+                   N, T, H, ldh, int(backwards), 5.0, 0, 0, ws.data_ptr(), nbytes, G.stream())
+        res.append((G.host(d_dg), G.host(d_dci), G.host(d_dhi), G.host(d_dpeep) if peep else None))
+    tol = 3e-4
+    for a, b, name in zip(res[0], res[1], ('dgates', 'dcell_init', 'dhid_init', 'dpeep')):
+        if a is not None:
+            assert G.relerr(a, b) < tol, (name, G.relerr(a, b))
+    dG = G.deinterleave_gates(res[0][0], H).astype(np.float64)
+    assert G.relerr(dG.sum(0), gr['b']) < tol
+    assert G.relerr((dG @ p['W_in'].astype(np.float64).T).reshape(N, T, I), dx_ref) < tol
+    assert G.relerr(res[0][1], gr['cell_init']) < tol and G.relerr(res[0][2], gr['hid_init']) < tol
+
+
 def test_lstm_fwd_tensor_core_orthogonal_weights():
     """With the models' own initialisation (orthogonal W_hid, lasagne.init.Orthogonal) the tensor-core recurrence holds the
     1e-5 gate of the FFMA kernel over T = 40."""
