@@ -506,40 +506,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tmem_ld32_issue(lane_base, v);
           tmem_ld_wait();
         }
+        {
+          // Coalesced store of the 32 x 32 chunk through this warp's staging tile in the (now idle) pipeline memory:
+          // thread = row writes its 8 float4 at XOR-swizzled positions (conflict-free), then every store instruction
+          // covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes.
+          float* stg = reinterpret_cast<float*>(smem) + warp * 1024;
+          if (row < p.M) {
+            float* cpo = p.C + (size_t)row * p.ldc + n0 + c0;
+            if (p.accumulate) {
+#pragma unroll
+              for (int j4 = 0; j4 < 32; j4 += 4) {
+                const float4 old = *reinterpret_cast<const float4*>(cpo + j4);
+                v[j4] += old.x; v[j4 + 1] += old.y; v[j4 + 2] += old.z; v[j4 + 3] += old.w;
+              }
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j4 = 0; j4 < 32; j4 += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + j4]);
+                v[j4] += b4.x; v[j4 + 1] += b4.y; v[j4 + 2] += b4.z; v[j4 + 3] += b4.w;
+              }
+            }
+            switch (p.act) {
+              case IPAVSR_ACT_LINEAR: break;
+              case IPAVSR_ACT_SIGMOID:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
+                break;
+              case IPAVSR_ACT_RECTIFY:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                break;
+              default:
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
+                break;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          {
+            const int rbase = m0 + q * 32, jj = lane & 7;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const int rr = 4 * qq + (lane >> 3);
+              const float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + ((jj ^ (rr & 7)) << 2));
+              if (rbase + rr < p.M)
+                *reinterpret_cast<float4*>(p.C + (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj) = o;
+            }
+          }
+          __syncwarp();
+        }
         if (row < p.M) {
-          float* cp = p.C + (size_t)row * p.ldc + n0 + c0;
-          if (p.accumulate) {
-#pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-              const float4 old = *reinterpret_cast<const float4*>(cp + j4);
-              v[j4] += old.x; v[j4 + 1] += old.y; v[j4 + 2] += old.z; v[j4 + 3] += old.w;
-            }
-          }
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + j4]);
-              v[j4] += b4.x; v[j4 + 1] += b4.y; v[j4 + 2] += b4.z; v[j4 + 3] += b4.w;
-            }
-          }
-          switch (p.act) {
-            case IPAVSR_ACT_LINEAR: break;
-            case IPAVSR_ACT_SIGMOID:
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
-              break;
-            case IPAVSR_ACT_RECTIFY:
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              break;
-            default:
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], p.act);
-              break;
-          }
-#pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4)
-            *reinterpret_cast<float4*>(cp + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
           if (p.amax != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) tile_max = fmaxf(tile_max, fabsf(v[j]));
