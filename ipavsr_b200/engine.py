@@ -226,6 +226,7 @@ class _Run(object):
         self.vals = {}
         self.saved = {}
         self.grads = {}
+        self.cat = {}           # ConcatLayer -> (materialised buffer, bound tensor)
         self.pending = {}       # layer -> CUDA event of work still running on a side stream
         self.bwd_ready = {}     # LSTM layer -> (event, dG) launched ahead of the backward walk
         self.keep = []          # buffers that must outlive the side-stream kernels
@@ -253,6 +254,26 @@ class Engine(object):
         for l in self.layers:
             if isinstance(l, L.LSTMLayer) and l.mask_incoming_index > 0:
                 self.mask_layers.add(l.input_layers[1])
+        # A ConcatLayer whose inputs are all LSTM outputs (late fusion) is materialised for free: every LSTM writes its
+        # hidden states straight into its column slice of one buffer, so the consumers run ONE projection GEMM over the
+        # whole width instead of a K-split of accumulating GEMMs (and one operand split instead of one per stream).
+        consumers = {}
+        for l in self.layers:
+            for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
+                if i is not None:
+                    consumers.setdefault(i, []).append(l)
+        self.cat_plan, self.cat_of = {}, {}
+        if os.environ.get('IPAVSR_MATERIALISE_CONCAT', '1') != '0':
+            for l in self.layers:
+                if (isinstance(l, L.ConcatLayer) and len(l.input_layers) > 1 and
+                        all(isinstance(i, L.LSTMLayer) and consumers.get(i) == [l] for i in l.input_layers)):
+                    offs, o = [], 0
+                    for i in l.input_layers:
+                        offs.append(o)
+                        o += i.num_units
+                    self.cat_plan[l] = (offs, o)
+                    for i, off in zip(l.input_layers, offs):
+                        self.cat_of[i] = (l, off)
         self.dropout_seed = 1234
         self.dropout_calls = 0
         self.world = None            # (rank, world_size, group) when data-parallel
@@ -612,12 +633,28 @@ class Engine(object):
                     mask = torch.ones(N, T, dtype=torch.uint8, device=self.device)
                 xw = self.new(N * T, 4 * H)
                 self._proj(segs, ar.mat((l, 'W_in')), xw, ar.mat((l, 'b')).ptr, 0)
-                out = self.new(N * T, H, zero=(_ld8(H) != H))
+                cat_bound = None
+                if l in self.cat_of:
+                    cl, coff = self.cat_of[l]
+                    if cl not in run.cat:
+                        total = self.cat_plan[cl][1]
+                        bound = torch.zeros(2, dtype=torch.float32, device=self.device)
+                        bound[0] = 1.0
+                        run.cat[cl] = (self.new(N * T, total, zero=(_ld8(total) != total)), bound)
+                    cat, cat_bound = run.cat[cl]
+                    out = DevMat(cat.t, cat.ptr + 4 * coff, N * T, H, cat.ld)
+                else:
+                    out = self.new(N * T, H, zero=(_ld8(H) != H))
                 gates = cell = hprev = None
                 if train:
                     gates = self.new(N * T, 4 * H)
                     cell = self.new(N * T, H)
-                    hprev = self.new(N * T, H, zero=(_ld8(H) != H))
+                    if out.ld != _ld8(H):
+                        # the kernels share one leading dimension between out and hprev: give hprev the concat's
+                        t_hp = torch.empty(N * T * out.ld, dtype=torch.float32, device=self.device)
+                        hprev = DevMat(t_hp, t_hp.data_ptr(), N * T, H, out.ld)
+                    else:
+                        hprev = self.new(N * T, H, zero=(_ld8(H) != H))
                     if cell.ld != H:       # cell is dense (ld = H) inside the kernels
                         cell = DevMat(cell.t, cell.ptr, N * T, H, H)
                 peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
@@ -657,7 +694,11 @@ class Engine(object):
                     bound = torch.zeros(2, dtype=torch.float32, device=self.device)
                     bound[0] = 1.0
                     _lib.call('ipavsr_amax', ar.mat((l, 'hid_init')).ptr, H, 1, H, bound.data_ptr(), st)
-                    self._amax[(out.ptr, out.rows, out.cols, out.ld)] = bound
+                    if cat_bound is not None:
+                        # the materialised concat is bounded by the largest of its LSTMs' bounds (atomic max, same stream)
+                        _lib.call('ipavsr_amax', ar.mat((l, 'hid_init')).ptr, H, 1, H, cat_bound.data_ptr(), st)
+                    else:
+                        self._amax[(out.ptr, out.rows, out.cols, out.ld)] = bound
                     if hprev is not None:
                         self._amax[(hprev.ptr, hprev.rows, hprev.cols, hprev.ld)] = bound.clone()
             elif isinstance(l, (L.ElemwiseSumLayer, L.AdaptiveElemwiseSumLayer)):
@@ -670,10 +711,16 @@ class Engine(object):
                 _lib.call('ipavsr_fuse_sum', ptrs, lds, len(ins), coeffs, out.ptr, out.ld, rows, F, st)
                 run.vals[l] = [out]
             elif isinstance(l, L.ConcatLayer):
-                segs = []
-                for i in l.input_layers:
-                    segs.extend(run.vals[i])
-                run.vals[l] = segs
+                if l in run.cat:
+                    cat, bound = run.cat[l]
+                    if self.gemm_mode == 4:
+                        self._amax[(cat.ptr, cat.rows, cat.cols, cat.ld)] = bound
+                    run.vals[l] = [cat]
+                else:
+                    segs = []
+                    for i in l.input_layers:
+                        segs.extend(run.vals[i])
+                    run.vals[l] = segs
             elif isinstance(l, L.SliceLayer):
                 x = self._single(run.vals[l.input_layer])
                 out = self.new(N, x.cols, zero=(_ld8(x.cols) != x.cols))
@@ -844,11 +891,16 @@ class Engine(object):
                 for i in l.input_layers:
                     self._pass_grad(run, i, gsegs)
             elif isinstance(l, L.ConcatLayer):
-                k = 0
-                for i in l.input_layers:
-                    n = len(run.vals[i])
-                    self._pass_grad(run, i, gsegs[k:k + n])
-                    k += n
+                if l in run.cat:
+                    g = gsegs[0]            # one buffer over the whole width: every LSTM reads its column slice
+                    for i, off in zip(l.input_layers, self.cat_plan[l][0]):
+                        self._pass_grad(run, i, [DevMat(g.t, g.ptr + 4 * off, g.rows, i.num_units, g.ld)])
+                else:
+                    k = 0
+                    for i in l.input_layers:
+                        n = len(run.vals[i])
+                        self._pass_grad(run, i, gsegs[k:k + n])
+                        k += n
             elif isinstance(l, L.SliceLayer):
                 g = gsegs[0]
                 x = run.vals[l.input_layer][0]
