@@ -40,10 +40,11 @@ def _ld8(c):
 
 class DevMat(object):
     """A (rows x cols) float32 device matrix with leading dimension ld; `t` keeps the storage alive."""
-    __slots__ = ('t', 'ptr', 'rows', 'cols', 'ld')
+    __slots__ = ('t', 'ptr', 'rows', 'cols', 'ld', 'chunks')
 
-    def __init__(self, t, ptr, rows, cols, ld):
+    def __init__(self, t, ptr, rows, cols, ld, chunks=None):
         self.t, self.ptr, self.rows, self.cols, self.ld = t, ptr, rows, cols, ld
+        self.chunks = chunks     # [(row0, nrows, upload event)] for an input that is still arriving in row chunks
 
     def row_slice(self, r0, n):
         return DevMat(self.t, self.ptr + 4 * r0 * self.ld, n, self.cols, self.ld)
@@ -262,6 +263,19 @@ class Engine(object):
             for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
                 if i is not None:
                     consumers.setdefault(i, []).append(l)
+        # host inputs that only feed a DenseLayer (an encoder's fc1) can be uploaded in row chunks with the first GEMM
+        # running chunk by chunk as they arrive (IPAVSR_CHUNKED_UPLOAD=1).  Off by default: measured, it does not help —
+        # what is exposed is the total PCIe time of all streams, which function(...).prefetch hides instead.
+        self.chunkable = set()
+        for l in self.layers:
+            if isinstance(l, L.InputLayer):
+                c = l
+                while consumers.get(c) and len(consumers[c]) == 1 and isinstance(consumers[c][0], L.ReshapeLayer):
+                    c = consumers[c][0]
+                cons = consumers.get(c, [])
+                if (len(cons) == 1 and isinstance(cons[0], L.DenseLayer) and cons[0].nonlinearity.name != 'softmax' and
+                        os.environ.get('IPAVSR_CHUNKED_UPLOAD', '0') == '1'):
+                    self.chunkable.add(l)
         self.cat_plan, self.cat_of = {}, {}
         if os.environ.get('IPAVSR_MATERIALISE_CONCAT', '1') != '0':
             for l in self.layers:
@@ -280,6 +294,7 @@ class Engine(object):
         self.step_t = np.float32(0)  # Adam's shared step counter (custom/updates.py:74)
         self._ws = None
         self._split_cache = {}
+        self._split_by_storage = {}
         self._amax = {}
         self._lr_cache = None
         # independent LSTM recurrences (the per-stream LSTMs; the forward/backward aggregate pair) run concurrently
@@ -288,6 +303,7 @@ class Engine(object):
         self._side = []
         self._side_next = 0
         self._copy_stream = None
+        self._prefetched = []
         self._c14 = None
         # fp16 hi/lo of sigmoid/tanh outputs written by the GEMM epilogue itself (static scale 2^14).  Off by default: with
         # the epilogue's row-per-thread store pattern the extra 8-byte stores cost more than the separate split pass saves.
@@ -396,7 +412,17 @@ class Engine(object):
                     ar.exps.data_ptr() + 4 * int(ar.seg_host[off // SEG]))
         key = (m.ptr, m.rows, m.cols, m.ld)
         hit = self._split_cache.get(key)
+        if hit is None and m.t is not None:
+            # a row range of a tensor that is already split as a whole shares its hi/lo arrays and scale
+            for pk in self._split_by_storage.get(id(m.t), ()):
+                pptr, prows, pcols, pld = pk
+                off = m.ptr - pptr
+                if (pk in self._split_cache and pld == m.ld and pcols == m.cols and off >= 0 and off % (4 * pld) == 0 and
+                        off // (4 * pld) + m.rows <= prows):
+                    ph = self._split_cache[pk]
+                    return ph[0].data_ptr() + off // 2, ph[1].data_ptr() + off // 2, ph[2].data_ptr() + 4
         if hit is None:
+            self._split_by_storage.setdefault(id(m.t), []).append(key)
             n = max(m.rows * m.ld, 8)
             hi = torch.empty(n, dtype=torch.float16, device=self.device)
             lo = torch.empty(n, dtype=torch.float16, device=self.device)
@@ -410,7 +436,8 @@ class Engine(object):
             self._split_cache[key] = hit
         return hit[0].data_ptr(), hit[1].data_ptr(), hit[2].data_ptr() + 4
 
-    def gemm(self, A, B, Cm, M, N, K, transA=0, transB=0, bias=None, act=0, accumulate=0, emit_split=False):
+    def gemm(self, A, B, Cm, M, N, K, transA=0, transB=0, bias=None, act=0, accumulate=0, emit_split=False,
+             amax_t=None):
         mode = self.gemm_mode
         if mode == 4:
             if not self.lib.ipavsr_gemm_f16_supported(M, N, K, 16, A.ld, 16, B.ld):
@@ -419,7 +446,9 @@ class Engine(object):
                 ah, al, ea = self._split16(A)
                 bh, bl, eb = self._split16(B)
                 amax = chi = clo = None
-                if emit_split and not accumulate:
+                if amax_t is not None:
+                    amax = amax_t.data_ptr()        # the caller collects max|C| over several row-chunk products
+                elif emit_split and not accumulate:
                     key = (Cm.ptr, Cm.rows, Cm.cols, Cm.ld)
                     if act in (1, 3) and self.epilogue_split:
                         # sigmoid / tanh outputs are bounded by 1: the epilogue writes the fp16 hi/lo split itself under
@@ -497,7 +526,61 @@ class Engine(object):
         d[:, :F].copy_(t.reshape(N * T, F), non_blocking=True)
         return DevMat(d, d.data_ptr(), N * T, F, ld)
 
-    def _stage_inputs(self, inputs):
+    @staticmethod
+    def _host_signature(inputs, layers):
+        sig = []
+        for l in layers:
+            a = inputs[l]
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    continue
+                sig.append((id(l), a.data_ptr(), tuple(a.shape)))
+            else:
+                a = np.asarray(a)
+                sig.append((id(l), a.__array_interface__['data'][0], tuple(a.shape)))
+        return tuple(sig)
+
+    def prefetch(self, inputs):
+        """Stage the host inputs of a later forward() now (function(...).prefetch)."""
+        staged = self._stage_inputs(inputs, allow_chunks=False)
+        if staged:
+            self._prefetched.append((self._host_signature(inputs, self.input_layers), staged))
+            del self._prefetched[:-4]          # a forgotten prefetch must not pin device memory for ever
+
+    def _take_prefetched(self, inputs):
+        if not self._prefetched:
+            return None
+        sig = self._host_signature(inputs, self.input_layers)
+        for i, (s, staged) in enumerate(self._prefetched):
+            if s == sig:
+                del self._prefetched[i]
+                return staged
+        return None
+
+    def _upload_chunked(self, arr, cs, nchunks=4):
+        """(N,T,F) host array -> device matrix filled by `nchunks` asynchronous row-chunk copies on stream `cs`, each with
+        its own event (DevMat.chunks).  None when the input is too small or needs a padded leading dimension."""
+        t = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(arr).astype(np.float32, copy=False)))
+        if t.dtype != torch.float32 or t.dim() != 3 or not t.is_contiguous():
+            return None
+        N, T, F = t.shape
+        if F % 8 != 0 or N * T < 8192 or N < 2 * nchunks:
+            return None
+        d = torch.empty(N * T, F, dtype=torch.float32, device=self.device)
+        h2 = t.reshape(N * T, F)
+        chunks, per = [], (N + nchunks - 1) // nchunks
+        for c in range(nchunks):
+            r0, r1 = c * per * T, min(N, (c + 1) * per) * T
+            if r1 <= r0:
+                break
+            d[r0:r1].copy_(h2[r0:r1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            chunks.append((r0, r1 - r0, ev))
+        return DevMat(d, d.data_ptr(), N * T, F, F, chunks=chunks)
+
+    def _stage_inputs(self, inputs, allow_chunks=True):
         """Host inputs are copied on a dedicated copy stream, all issued up front in graph order, so that the upload of
         the later streams overlaps the encoder of the first ones; the compute stream waits per input, on first use.
         Pinned host tensors make the copies truly asynchronous.  Returns {layer: (device value, event)}."""
@@ -515,7 +598,11 @@ class Engine(object):
         order = [l for l in host if l in self.mask_layers] + [l for l in host if l not in self.mask_layers]
         with torch.cuda.stream(cs):
             for l in order:
-                val = self._upload(inputs[l], 'mask' if l in self.mask_layers else 'float')
+                val = None
+                if allow_chunks and l in self.chunkable and self.gemm_mode == 4 and l not in self.mask_layers:
+                    val = self._upload_chunked(inputs[l], cs)
+                if val is None:
+                    val = self._upload(inputs[l], 'mask' if l in self.mask_layers else 'float')
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 (val if isinstance(val, torch.Tensor) else val.t).record_stream(main)
@@ -535,8 +622,9 @@ class Engine(object):
                 break
         N, T = int(first.shape[0]), int(first.shape[1])
         run = _Run(N, T)
-        staged = self._stage_inputs(inputs)
+        staged = self._take_prefetched(inputs) or self._stage_inputs(inputs)
         self._split_cache = {}
+        self._split_by_storage = {}
         self._amax = {}
         if self.gemm_mode in (1, 4):
             self._refresh_param_split()
@@ -550,7 +638,8 @@ class Engine(object):
             if isinstance(l, L.InputLayer):
                 if l in staged:
                     val, ev = staged[l]
-                    torch.cuda.current_stream(self.device).wait_event(ev)
+                    if not (isinstance(val, DevMat) and val.chunks):     # chunked inputs are awaited chunk by chunk
+                        torch.cuda.current_stream(self.device).wait_event(ev)
                     run.vals[l] = val if l in self.mask_layers else [val]
                 elif l in self.mask_layers:
                     run.vals[l] = self._upload(inputs[l], 'mask')
@@ -568,6 +657,15 @@ class Engine(object):
                     logits = self.new(rows, l.num_units)
                     self._proj(segs, W, logits, b, 0)
                     _lib.call('ipavsr_softmax', logits.ptr, logits.ld, out.ptr, out.ld, rows, l.num_units, st)
+                elif len(segs) == 1 and segs[0].chunks and self.gemm_mode == 4:
+                    # the input is still arriving: one product per row chunk, each split with its own scale
+                    x = segs[0]
+                    amax_t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                    for (r0, n, ev) in x.chunks:
+                        torch.cuda.current_stream(self.device).wait_event(ev)
+                        self.gemm(x.row_slice(r0, n), W, out.row_slice(r0, n), n, out.cols, x.cols, 0, 0, b,
+                                  ACT[l.nonlinearity.name], 0, amax_t=amax_t)
+                    self._amax[(out.ptr, out.rows, out.cols, out.ld)] = amax_t
                 else:
                     self._proj(segs, W, out, b, ACT[l.nonlinearity.name], emit_split=True)
                 run.vals[l] = [out]
@@ -967,6 +1065,14 @@ class Engine(object):
             tgt, acc = self._grad_target(run, in_layer, xsegs)
         k0 = 0
         for i, a in enumerate(xsegs):
+            if a.chunks and self.gemm_mode == 4 and len(xsegs) == 1:
+                # x was split chunk by chunk (one scale each): the weight gradient accumulates over the row chunks
+                self._split16(dZ)
+                for ci, (r0, n, _) in enumerate(a.chunks):
+                    self.gemm(a.row_slice(r0, n), dZ.row_slice(r0, n), dW, a.cols, dZ.cols, n, transA=1,
+                              accumulate=1 if ci > 0 else 0)
+                k0 += a.cols
+                continue
             self.gemm(a, dZ, dW.row_slice(k0, a.cols), a.cols, dZ.cols, a.rows, transA=1)
             if need_dx:
                 self.gemm(dZ, W.row_slice(k0, a.cols), tgt[i], a.rows, a.cols, dZ.cols, transB=1, accumulate=acc)
@@ -1044,6 +1150,7 @@ class Engine(object):
         ar, st = self.arena, self.stream
         ar.split_dirty = True
         self._split_cache = {}
+        self._split_by_storage = {}
         self._amax = {}
         n = ar.n
         seg_lr = seg_id = None

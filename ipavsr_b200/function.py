@@ -150,5 +150,20 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         eng.optim_step(u.kind, _lr_value(u.lr) if u.lr is not None else 0.0, params=u.params, lr_map=u.lr_map, **u.hp)
         return eng.read_loss()
 
+    def prefetch(*args, **kw):
+        """Start the host->device copy of the NEXT call's inputs (same positional arguments as the call itself) on the
+        engine's copy stream and return at once: the copy overlaps whatever the device is doing, and the matching call
+        picks the staged buffers up instead of copying again.  A double-buffered loader in two lines:
+
+            train.prefetch(*batch[0])
+            for i in range(n):
+                if i + 1 < n: train.prefetch(*batch[i + 1])
+                cost = train(*batch[i])
+        """
+        if len(args) != len(slots):
+            raise TypeError('expected %d arguments, got %d' % (len(slots), len(args)))
+        eng.prefetch({layer: a for (kind, layer), a in zip(slots, args) if kind == 'input'})
+
     fn.engine = eng
+    fn.prefetch = prefetch
     return fn

@@ -118,6 +118,12 @@ def test_deterministic_eval_and_val_fn_api():
     assert got.shape == ref.shape and got.dtype == np.float32
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-4
     assert (got.argmax(-1) == ref.argmax(-1)).all()
+    # double-buffered input staging: a prefetched call returns the same result and consumes the staged buffers
+    val_fn.prefetch(feed['input'], mask, feed['dct'], win)
+    assert len(val_fn.engine._prefetched) == 1
+    got_pf = val_fn(feed['input'], mask, feed['dct'], win)
+    np.testing.assert_array_equal(got_pf, got)
+    assert len(val_fn.engine._prefetched) == 0
     # float64 / wide-int inputs are downcast like allow_input_downcast=True
     got2 = val_fn(feed['input'].astype('float64'), mask.astype('int64'), feed['dct'].astype('float64'), win)
     np.testing.assert_allclose(got2, got, rtol=1e-6, atol=1e-7)
