@@ -30,14 +30,16 @@ __device__ __forceinline__ float delta_step(float acc, float diff, int th) {
     // for a power-of-two theta the product diff * (1/(2 theta)) is exact; otherwise one Markstein correction step
     // (q = d*r; rem = fma(-q, c, d) exact; q' = fma(rem, r, q)) gives the correctly rounded quotient for these small
     // integer divisors c.
+    // Power-of-two theta: the term diff / (2 theta) is exact in float32 and float32(float64(acc) + term) equals the single
+    // rounding of a float32 FMA (a float64 sum of two float32 values only rounds when they are > 2^29 apart, where no
+    // float32 rounding boundary is near), so those steps need no float64 arithmetic at all.
+    if ((th & (th - 1)) == 0) return fmaf(diff, 1.0f / (2.0f * (float)th), acc);
     const double c = 2.0 * (double)th;
     const double r = 1.0 / c;
     const double d = (double)diff;
     double q = d * r;
-    if ((th & (th - 1)) != 0) {
-      const double rem = fma(-q, c, d);
-      q = fma(rem, r, q);
-    }
+    const double rem = fma(-q, c, d);
+    q = fma(rem, r, q);
     return (float)((double)acc + q);
   } else {
     return fmaf(diff, 1.0f / (2.0f * (float)th), acc);
@@ -175,6 +177,218 @@ __global__ void __launch_bounds__(DELTA_THREADS) delta_bwd_kernel(const float* _
     }
     __syncthreads();
   }
+}
+
+// Backward as a GATHER (the production kernel; the scatter form above is kept as the cross-check).  With c_th = 1/(2 th)
+// and v zero outside [0, T):
+//     (D^T v)[s] = sum_th c_th (v[s-th] - v[s+th])                          0 < s < T-1
+//     (D^T v)[T-1] = sum_th c_th sum_{t = max(0, T-1-th)}^{T-1} v[t]         (everything the forward clamped onto T-1)
+//     (D^T v)[0]   = - sum_th c_th sum_{t = 0}^{min(th, T-1)} v[t]          (everything clamped onto 0)
+// A CTA stages the [g_x | g_d | g_a] rows of `upc` utterances in shared memory (coalesced), every thread owns a run of 4
+// frames of one feature and slides a register window over it (lanes walk the feature axis: conflict-free), twice.
+constexpr int DBW_RUN = 4;
+
+template <int TH>
+__device__ __forceinline__ void delta_T_gather(const float* __restrict__ v, const float* __restrict__ base,
+                                               float* __restrict__ out, int T, int F, int theta, int tid, int nthreads) {
+  // out[s][f] = base[s][f] + (D^T v)[s][f]   (out may alias base)
+  const int runs = (T + DBW_RUN - 1) / DBW_RUN;
+  const int items = runs * F;
+  const int th_n = TH > 0 ? TH : theta;
+  for (int it = tid; it < items; it += nthreads) {
+    const int f = it % F;
+    const int s0 = (it / F) * DBW_RUN;
+    float w[2 * (TH > 0 ? TH : 1) + DBW_RUN];
+    if (TH > 0) {
+#pragma unroll
+      for (int i = 0; i < 2 * TH + DBW_RUN; ++i) {
+        const int t = s0 - TH + i;
+        w[i] = (t >= 0 && t < T) ? v[t * F + f] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < DBW_RUN; ++r) {
+      const int s = s0 + r;
+      if (s >= T) break;
+      float acc = 0.f;
+      if (T > 1 && s == T - 1) {
+        float run = v[(T - 1) * F + f];
+        for (int th = 1; th <= th_n; ++th) {
+          if (T - 1 - th >= 0) run += v[(T - 1 - th) * F + f];
+          acc = fmaf(run, 1.0f / (2.0f * (float)th), acc);
+        }
+      } else if (T > 1 && s == 0) {
+        float run = v[f];
+        for (int th = 1; th <= th_n; ++th) {
+          if (th <= T - 1) run += v[th * F + f];
+          acc = fmaf(-run, 1.0f / (2.0f * (float)th), acc);
+        }
+      } else if (T > 1) {
+        if (TH > 0) {
+#pragma unroll
+          for (int th = 1; th <= TH; ++th) acc = fmaf(w[r + TH - th] - w[r + TH + th], 1.0f / (2.0f * (float)th), acc);
+        } else {
+          for (int th = 1; th <= theta; ++th) {
+            const float lo = s - th >= 0 ? v[(s - th) * F + f] : 0.f;
+            const float hi = s + th < T ? v[(s + th) * F + f] : 0.f;
+            acc = fmaf(lo - hi, 1.0f / (2.0f * (float)th), acc);
+          }
+        }
+      }
+      out[s * F + f] = base[s * F + f] + acc;
+    }
+  }
+}
+
+template <int TH>
+__global__ void __launch_bounds__(DELTA_THREADS) delta_bwd_gather_kernel(const float* __restrict__ gy, int ldgy,
+                                                                         float* __restrict__ gx, int ldgx, int N, int T,
+                                                                         int F, int theta, int upc, int accumulate) {
+  extern __shared__ __align__(16) float sm[];
+  const int TF = T * F;
+  float* s_a = sm;                      // g_a
+  float* s_d = sm + (size_t)upc * TF;   // g_d, then u = g_d + D^T g_a
+  float* s_x = s_d + (size_t)upc * TF;  // g_x, then g_x + D^T u
+  const int tid = threadIdx.x;
+  const int F3 = 3 * F;
+  const bool vec = (F % 4 == 0) && (ldgy % 4 == 0) && ((reinterpret_cast<uintptr_t>(gy) & 15) == 0);
+  for (int u0 = blockIdx.x * upc; u0 < N; u0 += gridDim.x * upc) {
+    const int nu = min(upc, N - u0);
+    const int rows = nu * T;
+    if (vec) {
+      const int F34 = F3 / 4;
+      for (int i = tid; i < rows * F34; i += DELTA_THREADS) {
+        const int r = i / F34, c = (i - r * F34) * 4;
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(gy + ((size_t)u0 * T + r) * ldgy + c));
+        float* dst = c < F ? s_x + r * F + c : (c < 2 * F ? s_d + r * F + (c - F) : s_a + r * F + (c - 2 * F));
+        *reinterpret_cast<float4*>(dst) = v;
+      }
+    } else {
+      for (int i = tid; i < rows * F3; i += DELTA_THREADS) {
+        const int r = i / F3, c = i - r * F3;
+        const float v = __ldcs(gy + ((size_t)u0 * T + r) * ldgy + c);
+        if (c < F) s_x[r * F + c] = v;
+        else if (c < 2 * F) s_d[r * F + (c - F)] = v;
+        else s_a[r * F + (c - 2 * F)] = v;
+      }
+    }
+    __syncthreads();
+    for (int u = 0; u < nu; ++u) delta_T_gather<TH>(s_a + u * TF, s_d + u * TF, s_d + u * TF, T, F, theta, tid, DELTA_THREADS);
+    __syncthreads();
+    for (int u = 0; u < nu; ++u) delta_T_gather<TH>(s_d + u * TF, s_x + u * TF, s_x + u * TF, T, F, theta, tid, DELTA_THREADS);
+    __syncthreads();
+    for (int i = tid; i < rows * F; i += DELTA_THREADS) {
+      const int r = i / F, c = i - r * F;
+      float* o = gx + ((size_t)u0 * T + r) * ldgx + c;
+      const float v = s_x[r * F + c];
+      *o = accumulate ? *o + v : v;
+    }
+    __syncthreads();
+  }
+}
+
+// Register-resident column form of the gather (T <= 48, Theta in {1,4,9}): one THREAD owns one (utterance, feature)
+// column, zero-padded by Theta on both sides so that every register index is static.  Rows 0 and T-1 collect what the
+// forward clamped onto them: row 0 has a static formula; row T-1 sits at a runtime index, so its value is formed as
+// sum_t v[t] * wtab[T-1-t] with a small constant table (the index is uniform over the launch: constant-cache broadcast)
+// and selected when the row is written.  No shared memory, no barriers.
+__constant__ float c_dbw_tab[64];      // wtab[d] = sum_{th = max(d,1)}^{Theta} 1/(2 th) for 0 <= d <= Theta, else 0
+
+template <int TH, int TMAX>
+__device__ __forceinline__ void delta_T_col(const float (&v)[TMAX + 2 * TH], float (&y)[TMAX], int T) {
+  // v[i] holds frame i - TH (zero outside [0, T)); y[s] = (D^T v)[s] for s < T (garbage beyond)
+  float last = 0.f;
+#pragma unroll
+  for (int t = 0; t < TMAX; ++t) {
+    const int d = T - 1 - t;
+    last = fmaf(v[t + TH], (d >= 0 && d <= TH) ? c_dbw_tab[d] : 0.f, last);
+  }
+#pragma unroll
+  for (int s = 0; s < TMAX; ++s) {
+    float acc = 0.f;
+    if (s == 0) {
+      float run = v[TH];
+#pragma unroll
+      for (int th = 1; th <= TH; ++th) {
+        run += v[TH + th];
+        acc = fmaf(-run, 1.0f / (2.0f * (float)th), acc);
+      }
+    } else {
+#pragma unroll
+      for (int th = 1; th <= TH; ++th) acc = fmaf(v[s + TH - th] - v[s + TH + th], 1.0f / (2.0f * (float)th), acc);
+    }
+    y[s] = (T > 1) ? ((s == T - 1) ? last : acc) : 0.f;
+  }
+}
+
+template <int TH, int TMAX>
+__global__ void __launch_bounds__(128) delta_bwd_col_kernel(const float* __restrict__ gy, int ldgy, float* __restrict__ gx,
+                                                            int ldgx, int N, int T, int F, int accumulate) {
+  const long long total = (long long)N * F;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+       c += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(c / F), f = (int)(c % F);
+    const float* gc = gy + (size_t)n * T * ldgy + f;
+    float* oc = gx + (size_t)n * T * ldgx + f;
+    float v[TMAX + 2 * TH], y[TMAX], w[TMAX];
+    // both gradient columns are requested up front (80 independent loads in flight per thread), g_x right after
+#pragma unroll
+    for (int i = 0; i < TMAX + 2 * TH; ++i) {
+      const int t = i - TH;
+      v[i] = (t >= 0 && t < T) ? __ldg(gc + (size_t)t * ldgy + 2 * F) : 0.f;      // g_a
+    }
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) w[t] = t < T ? __ldg(gc + (size_t)t * ldgy + F) : 0.f;      // g_d
+    delta_T_col<TH, TMAX>(v, y, T);
+#pragma unroll
+    for (int i = 0; i < TMAX + 2 * TH; ++i) {
+      const int t = i - TH;
+      v[i] = (t >= 0 && t < TMAX && t < T) ? w[t >= 0 && t < TMAX ? t : 0] + y[t >= 0 && t < TMAX ? t : 0] : 0.f;   // u
+    }
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t) w[t] = t < T ? __ldg(gc + (size_t)t * ldgy) : 0.f;          // g_x
+    delta_T_col<TH, TMAX>(v, y, T);
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+      if (t < T) {
+        const float o = w[t] + y[t];
+        float* dst = oc + (size_t)t * ldgx;
+        if (accumulate) *dst += o;
+        else __stcs(dst, o);
+      }
+  }
+}
+
+template <int TH, int TMAX>
+static int launch_delta_bwd_col(const float* gy, int ldgy, float* gx, int ldgx, int N, int T, int F, int accumulate,
+                                cudaStream_t st) {
+  static int tab_theta = -1;
+  if (tab_theta != TH) {
+    float tab[64];
+    for (int d = 0; d < 64; ++d) {
+      float s = 0.f;
+      if (d <= TH)
+        for (int th = (d > 1 ? d : 1); th <= TH; ++th) s += 1.0f / (2.0f * (float)th);
+      tab[d] = s;
+    }
+    IPAVSR_CUDA(cudaMemcpyToSymbolAsync(c_dbw_tab, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
+    tab_theta = TH;
+  }
+  const long long total = (long long)N * F;
+  long long blocks = (total + 127) / 128;
+  const long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  delta_bwd_col_kernel<TH, TMAX><<<(int)blocks, 128, 0, st>>>(gy, ldgy, gx, ldgx, N, T, F, accumulate);
+  IPAVSR_LAUNCH_CHECK();
+  return IPAVSR_OK;
+}
+
+template <int TH>
+static int dispatch_delta_bwd_col(const float* gy, int ldgy, float* gx, int ldgx, int N, int T, int F, int accumulate,
+                                  cudaStream_t st) {
+  if (T <= 24) return launch_delta_bwd_col<TH, 24>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);
+  if (T <= 40) return launch_delta_bwd_col<TH, 40>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);
+  return launch_delta_bwd_col<TH, 48>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -519,9 +733,36 @@ int ipavsr_delta_bwd(const float* gy, int ldgy, float* gx, int ldgx, int N, int 
   int blocks_needed = (N + upc - 1) / upc;
   int cap = sm_count() * 6;
   int grid = blocks_needed < cap ? blocks_needed : cap;
-  if (smem > 48 * 1024)
-    IPAVSR_CUDA(cudaFuncSetAttribute(delta_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  delta_bwd_kernel<<<grid, DELTA_THREADS, smem, st>>>(gy, ldgy, gx, ldgx, N, T, F, theta, upc, accumulate);
+  static int use_scatter = -1;          // IPAVSR_DELTA_BWD=scatter|tile selects the first-cut / shared-memory kernels
+  if (use_scatter < 0) {
+    const char* e = getenv("IPAVSR_DELTA_BWD");
+    use_scatter = (e && e[0] == 's') ? 1 : ((e && e[0] == 't') ? 2 : 0);
+  }
+  if (use_scatter == 0 && T <= 48 && (theta == 1 || theta == 4 || theta == 9)) {
+    if (theta == 1) return dispatch_delta_bwd_col<1>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);
+    if (theta == 4) return dispatch_delta_bwd_col<4>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);
+    return dispatch_delta_bwd_col<9>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);
+  }
+  if (use_scatter == 1) {
+    if (smem > 48 * 1024)
+      IPAVSR_CUDA(cudaFuncSetAttribute(delta_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    delta_bwd_kernel<<<grid, DELTA_THREADS, smem, st>>>(gy, ldgy, gx, ldgx, N, T, F, theta, upc, accumulate);
+    IPAVSR_LAUNCH_CHECK();
+    return IPAVSR_OK;
+  }
+#define IPAVSR_DBW_CASE(TH)                                                                                        \
+  do {                                                                                                            \
+    auto k = delta_bwd_gather_kernel<TH>;                                                                         \
+    if (smem > 48 * 1024) IPAVSR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k<<<grid, DELTA_THREADS, smem, st>>>(gy, ldgy, gx, ldgx, N, T, F, theta, upc, accumulate);                     \
+  } while (0)
+  switch (theta) {
+    case 1: IPAVSR_DBW_CASE(1); break;
+    case 4: IPAVSR_DBW_CASE(4); break;
+    case 9: IPAVSR_DBW_CASE(9); break;
+    default: IPAVSR_DBW_CASE(0); break;
+  }
+#undef IPAVSR_DBW_CASE
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }

@@ -147,6 +147,47 @@ __global__ void __launch_bounds__(256) featurewise_apply_kernel(const float* __r
   for (int64_t r = r0 + rl; r < r1; r += 8) __stcs(y + r * ldy + c, (__ldcs(x + r * ldx + c) - m) / sd);
 }
 
+// vectorised form: a thread owns 4 consecutive features (mean/std in registers) of every row of its row stripe, so a
+// warp streams 512 contiguous bytes per row (F % 4 == 0, 16-byte aligned rows)
+__global__ void __launch_bounds__(256) featurewise_apply_vec_kernel(const float* __restrict__ x, int ldx,
+                                                                    const float* __restrict__ mean,
+                                                                    const float* __restrict__ std, float* __restrict__ y,
+                                                                    int ldy, int64_t frames, int F4) {
+  const int64_t total = frames * F4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F4;
+    const int c = (int)(i - r * F4) << 2;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(x + r * ldx + c));
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c));
+    const float4 s = __ldg(reinterpret_cast<const float4*>(std + c));
+    __stcs(reinterpret_cast<float4*>(y + r * ldy + c),
+           make_float4((v.x - m.x) / s.x, (v.y - m.y) / s.y, (v.z - m.z) / s.z, (v.w - m.w) / s.w));
+  }
+}
+
+// compute_diff_images, vectorised: block = (utterance, row stripe); every thread produces float4s y[r] = x[r] - x[r-1]
+// (the second read of a row hits L1/L2), y[first] = x[first+1] - x[first] (the reference duplicates the first difference)
+__global__ void __launch_bounds__(256) diff_image_vec_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y,
+                                                             int ldy, const int64_t* __restrict__ offsets, int D4) {
+  const int u = blockIdx.y;
+  const int64_t b = offsets[u], e = offsets[u + 1];
+  const int64_t len = e - b;
+  if (len <= 0) return;
+  const int64_t total = len * D4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / D4;
+    const int c = (int)(i - t * D4) << 2;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (len > 1) {
+      const int64_t r = b + (t == 0 ? 1 : t);
+      const float4 cur = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c));
+      const float4 prv = __ldg(reinterpret_cast<const float4*>(x + (r - 1) * ldx + c));
+      o = make_float4(cur.x - prv.x, cur.y - prv.y, cur.z - prv.z, cur.w - prv.w);
+    }
+    __stcs(reinterpret_cast<float4*>(y + (b + t) * ldy + c), o);
+  }
+}
+
 // ---- a12 sequencewise_mean_image_subtraction (:260-277) and a14 compute_diff_images (:506-517) ----
 // grid (column chunks of 128, utterances); a thread owns one pixel column of one utterance and walks its frames in
 // order, which reproduces numpy's sequential float32 axis-0 summation exactly.
@@ -283,6 +324,13 @@ int ipavsr_norm_featurewise_apply(const float* x, int ldx, const float* mean, co
                                   int64_t frames, int F, void* stream) {
   IPAVSR_CHECK_ARG(x && mean && std && y && frames >= 0 && F >= 1, "bad arguments");
   if (frames == 0) return IPAVSR_OK;
+  if (F % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(mean) && aligned16(std)) {
+    const int64_t items = frames * (F / 4);
+    featurewise_apply_vec_kernel<<<grid_cap((items + 255) / 256, 16), 256, 0, S(stream)>>>(x, ldx, mean, std, y, ldy,
+                                                                                           frames, F / 4);
+    IPAVSR_LAUNCH_CHECK();
+    return IPAVSR_OK;
+  }
   int rows_per_block = 64;
   while ((frames + rows_per_block - 1) / rows_per_block > 60000) rows_per_block *= 2;
   dim3 grid((F + 31) / 32, (unsigned)((frames + rows_per_block - 1) / rows_per_block));
@@ -306,6 +354,13 @@ int ipavsr_diff_image(const float* x, int ldx, float* y, int ldy, const int64_t*
   IPAVSR_CHECK_ARG(x && y && offsets && U >= 0 && D >= 1, "bad arguments");
   if (U == 0) return IPAVSR_OK;
   IPAVSR_CHECK_ARG(U <= 65535, "at most 65535 utterances per call");
+  if (D % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && aligned16(x) && aligned16(y)) {
+    // ~4 blocks per utterance of typical length (40 frames x 300 float4) keep every SM busy with coalesced row streams
+    dim3 grid(4, U);
+    diff_image_vec_kernel<<<grid, 256, 0, S(stream)>>>(x, ldx, y, ldy, offsets, D / 4);
+    IPAVSR_LAUNCH_CHECK();
+    return IPAVSR_OK;
+  }
   dim3 grid((D + 127) / 128, U);
   diff_image_kernel<<<grid, 128, 0, S(stream)>>>(x, ldx, y, ldy, offsets, D);
   IPAVSR_LAUNCH_CHECK();
