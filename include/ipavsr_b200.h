@@ -155,12 +155,16 @@ int ipavsr_lstm_fwd_f16(const float* xw, const uint16_t* whid_hi, const uint16_t
 int ipavsr_lstm_fwd_f16_supported(int N, int T, int H, int ldw);
 /* Tensor-core form of ipavsr_lstm_bwd (same results; needs clip > 0: the clipped gate gradients are the fp16 operand
  * of the recurrent product, scaled by a power of two chosen from `clip`).  w_hid is the float32 matrix (the host-side
- * d(hid_init) product), whid_hi/lo/exp its fp16 split; workspace >= 2*N*H floats. */
+ * d(hid_init) product), whid_hi/lo/exp its fp16 split; workspace >= 2*N*H floats.
+ * Optional by-products that save later passes over dgates: db (4H, gate-interleaved; (+)= column sums of dgates = the
+ * bias gradient) and dg_hi/dg_lo/dg_exp = the fp16 split of dgates (dense (N*T, 4H) halves + its scale exponent),
+ * which the kernel forms anyway as the operand of its recurrent product. */
 int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* whid_hi, const uint16_t* whid_lo,
                         const int32_t* whid_exp, int ldw, const float* peep, const float* cell_init, const uint8_t* mask,
                         const float* gates, const float* cell, float* dgates, float* dpeep, float* dcell_init,
                         float* dhid_init, int N, int T, int H, int ldh, int backwards, float clip, int accumulate,
-                        void* workspace, uint64_t workspace_bytes, void* stream);
+                        float* db, uint16_t* dg_hi, uint16_t* dg_lo, int32_t* dg_exp, void* workspace,
+                        uint64_t workspace_bytes, void* stream);
 int ipavsr_lstm_bwd_f16_supported(int N, int T, int H, int ldw, float clip);
 
 /* ---- a4/a5/a7: fusion, merge, slice, dropout ---------------------------------------------------------- */

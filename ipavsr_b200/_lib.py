@@ -43,7 +43,7 @@ _SIGS = {
     'ipavsr_lstm_workspace_bytes': (U64, [I, I, I]),
     'ipavsr_lstm_fwd_f16': (I, [P, P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, I, I, P]),
     'ipavsr_lstm_fwd_f16_supported': (I, [I, I, I, I]),
-    'ipavsr_lstm_bwd_f16': (I, [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P, U64, P]),
+    'ipavsr_lstm_bwd_f16': (I, [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P, P, P, P, P, U64, P]),
     'ipavsr_lstm_bwd_f16_supported': (I, [I, I, I, I, F]),
     'ipavsr_fuse_sum': (I, [P, P, I, P, P, I, I, I, P]),
     'ipavsr_adasum_bwd_coeff': (I, [P, I, P, P, I, P, I, I, I, P]),

@@ -521,7 +521,8 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
                    const float* __restrict__ cell_init, const uint8_t* __restrict__ mask, const float* __restrict__ gates,
                    const float* __restrict__ cell, float* __restrict__ dgates, float* __restrict__ dpeep,
                    float* __restrict__ dc_fin, float* __restrict__ dh_fin, int N, int T, int H, int ldh, int backwards,
-                   float clip, int eg) {
+                   float clip, int eg, float* __restrict__ db, uint16_t* __restrict__ dg_hi, uint16_t* __restrict__ dg_lo,
+                   int32_t* __restrict__ dg_exp) {
   const int CS = (int)q_cluster_size();
   const int rank = (int)q_cluster_rank();
   const int tile = blockIdx.x / CS;
@@ -620,6 +621,8 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
     }
     float dh_next[4] = {0.f, 0.f, 0.f, 0.f}, dc_next[4] = {0.f, 0.f, 0.f, 0.f}, dh_pass[4] = {0.f, 0.f, 0.f, 0.f};
     float pci = 0.f, pcf = 0.f, pco = 0.f;
+    float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);      // bias gradient of my unit's 4 gates over my utterances and all steps
+    if (dg_exp != nullptr && blockIdx.x == 0 && tid == 0) *dg_exp = eg;
     float pf_dout[4], pf_c[4], pf_cp[4];
     float4 pf_g[4];
     bool pf_m[4];
@@ -659,6 +662,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
           dh_pass[i] = g.dh_pass;
           pci += g.pci; pcf += g.pcf; pco += g.pco;
           *reinterpret_cast<float4*>(dgates + row * H4 + 4 * ug) = dg;
+          dbs.x += dg.x; dbs.y += dg.y; dbs.z += dg.z; dbs.w += dg.w;
         }
         // operand tile: row n = 4 nq + i, columns j = 4 ul .. 4 ul + 3 (8 bytes), 128-byte rows, 128B swizzle
         const float v[4] = {dg.x * gs, dg.y * gs, dg.z * gs, dg.w * gs};
@@ -667,6 +671,12 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         for (int q = 0; q < 4; ++q) {
           h[q] = __float2half_rn(v[q]);
           l[q] = __float2half_rn((v[q] - __half2float(h[q])) * 2048.0f);
+        }
+        if (dg_hi != nullptr && n_ok[i] && u_ok) {
+          // the same fp16 hi/lo pair is the split of dgates for the weight-gradient GEMMs that follow: no split pass
+          const size_t o = ((size_t)ng[i] * T + t) * H4 + 4 * ug;
+          *reinterpret_cast<uint2*>(dg_hi + o) = *reinterpret_cast<const uint2*>(h);
+          *reinterpret_cast<uint2*>(dg_lo + o) = *reinterpret_cast<const uint2*>(l);
         }
         const int n = 4 * nq + i;
         const uint32_t off = (uint32_t)(ul >> 4) * 4096u + (uint32_t)n * 128u +
@@ -732,6 +742,12 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       atomicAdd(dpeep + ug, pci);
       atomicAdd(dpeep + H + ug, pcf);
       atomicAdd(dpeep + 2 * H + ug, pco);
+    }
+    if (db != nullptr && u_ok) {
+      atomicAdd(db + 4 * ug, dbs.x);
+      atomicAdd(db + 4 * ug + 1, dbs.y);
+      atomicAdd(db + 4 * ug + 2, dbs.z);
+      atomicAdd(db + 4 * ug + 3, dbs.w);
     }
   }
   q_fence_before();
@@ -844,7 +860,10 @@ int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* w
                         const int32_t* whid_exp, int ldw, const float* peep, const float* cell_init, const uint8_t* mask,
                         const float* gates, const float* cell, float* dgates, float* dpeep, float* dcell_init,
                         float* dhid_init, int N, int T, int H, int ldh, int backwards, float clip, int accumulate,
-                        void* workspace, uint64_t workspace_bytes, void* stream) {
+                        float* db, uint16_t* dg_hi, uint16_t* dg_lo, int32_t* dg_exp, void* workspace,
+                        uint64_t workspace_bytes, void* stream) {
+  IPAVSR_CHECK_ARG((dg_hi == nullptr) == (dg_lo == nullptr) && (dg_hi == nullptr) == (dg_exp == nullptr),
+                   "dg_hi, dg_lo and dg_exp go together");
   IPAVSR_CHECK_ARG(dout && w_hid && whid_hi && whid_lo && whid_exp && cell_init && mask && gates && cell && dgates &&
                        dcell_init && dhid_init,
                    "null pointer");
@@ -861,6 +880,7 @@ int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* w
     IPAVSR_CUDA(cudaMemsetAsync(dcell_init, 0, sizeof(float) * H, st));
     IPAVSR_CUDA(cudaMemsetAsync(dhid_init, 0, sizeof(float) * H, st));
     if (dpeep) IPAVSR_CUDA(cudaMemsetAsync(dpeep, 0, sizeof(float) * 3 * H, st));
+    if (db) IPAVSR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * 4 * H, st));
   }
   if (N == 0) return IPAVSR_OK;
   QEncodeFn enc = q_get_encode();
@@ -906,7 +926,8 @@ int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* w
   cfg.attrs = at;
   cfg.numAttrs = 1;
   IPAVSR_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_tc_kernel, maps[0], maps[1], dout, whid_exp, peep, cell_init, mask, gates,
-                                 cell, dgates, dpeep, dc_fin, dh_fin, N, T, H, ldh, backwards, clip, eg));
+                                 cell, dgates, dpeep, dc_fin, dh_fin, N, T, H, ldh, backwards, clip, eg, db, dg_hi, dg_lo,
+                                 dg_exp));
   count_launch();
   // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step
   const int t_first = backwards ? T - 1 : 0;

@@ -228,6 +228,7 @@ class _Run(object):
         self.saved = {}
         self.grads = {}
         self.cat = {}           # ConcatLayer -> (materialised buffer, bound tensor)
+        self.lstm_db_done = set()   # LSTMs whose bias gradient the backward kernel produced itself
         self.pending = {}       # layer -> CUDA event of work still running on a side stream
         self.bwd_ready = {}     # LSTM layer -> (event, dG) launched ahead of the backward walk
         self.keep = []          # buffers that must outlive the side-stream kernels
@@ -966,7 +967,8 @@ class Engine(object):
                 if not l.learn_init:
                     G((l, 'cell_init')).torch_view().zero_()
                     G((l, 'hid_init')).torch_view().zero_()
-                _lib.call('ipavsr_colsum', dG.ptr, dG.ld, G((l, 'b')).ptr, N * T, 4 * H, 0, st)
+                if l not in run.lstm_db_done:
+                    _lib.call('ipavsr_colsum', dG.ptr, dG.ld, G((l, 'b')).ptr, N * T, 4 * H, 0, st)
                 # dW_hid = hprev^T dG
                 self.gemm(hprev, dG, G((l, 'W_hid')), H, 4 * H, N * T, transA=1)
                 self._proj_bwd(run, l.input_layers[0], run.vals[l.input_layers[0]], dG, ar.mat((l, 'W_in')),
@@ -1046,10 +1048,22 @@ class Engine(object):
         if (self.gemm_mode == 4 and self.lstm_impl == 0 and
                 lib.ipavsr_lstm_bwd_f16_supported(N, T, H, whid.ld, float(clip))):
             wh, wl, we = self._split16(whid)
+            # by-products of the kernel: the bias gradient and the fp16 split of dgates (dense 4H-wide rows)
+            ghi = glo = gex = None
+            if dG.ld == 4 * H:
+                n = max(dG.rows * dG.ld, 8)
+                ghi = torch.empty(n, dtype=torch.float16, device=self.device)
+                glo = torch.empty(n, dtype=torch.float16, device=self.device)
+                gex = torch.zeros(2, dtype=torch.float32, device=self.device)
+                self._split_cache[(dG.ptr, dG.rows, dG.cols, dG.ld)] = (ghi, glo, gex, dG.t)
+                self._split_by_storage.setdefault(id(dG.t), []).append((dG.ptr, dG.rows, dG.cols, dG.ld))
             _lib.call('ipavsr_lstm_bwd_f16', dout.ptr, whid.ptr, wh, wl, we, whid.ld, peep, ar.mat((l, 'cell_init')).ptr,
                       mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,
                       G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
+                      G((l, 'b')).ptr, ghi.data_ptr() if ghi is not None else None,
+                      glo.data_ptr() if glo is not None else None, gex.data_ptr() + 4 if gex is not None else None,
                       ws.data_ptr(), int(nbytes), stream_handle)
+            run.lstm_db_done.add(l)
         else:
             _lib.call('ipavsr_lstm_bwd', dout.ptr, whid.ptr, peep, ar.mat((l, 'cell_init')).ptr,
                       mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep, G((l, 'cell_init')).ptr,

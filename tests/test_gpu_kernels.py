@@ -268,6 +268,9 @@ def test_lstm_bwd_tensor_core(N, T, H, peep, backwards, scale):
     dop[:, :H] = dout.reshape(N * T, H)
     d_dout = G.dev(dop)
     res = []
+    d_db = G.zeros((4 * H,))
+    dgh, dgl = G.zeros((N * T, 4 * H), torch.float16), G.zeros((N * T, 4 * H), torch.float16)
+    dge = G.zeros((1,), torch.int32)
     for tc in (True, False):
         d_dg, d_dpeep = G.zeros((N * T, 4 * H)), (G.zeros((3, H)) if peep else None)
         d_dci, d_dhi = G.zeros((H,)), G.zeros((H,))
@@ -276,7 +279,13 @@ def test_lstm_bwd_tensor_core(N, T, H, peep, backwards, scale):
             G.call('ipavsr_lstm_bwd_f16', d_dout.data_ptr(), d_whid.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4,
                    ldw, G.ptr(d_peep), d_ci.data_ptr(), d_mask.data_ptr(), d_gates.data_ptr(), d_cell.data_ptr(),
                    d_dg.data_ptr(), G.ptr(d_dpeep), d_dci.data_ptr(), d_dhi.data_ptr(), N, T, H, ldh, int(backwards), 5.0, 0,
-                   ws.data_ptr(), nbytes, G.stream())
+                   d_db.data_ptr(), dgh.data_ptr(), dgl.data_ptr(), dge.data_ptr(), ws.data_ptr(), nbytes, G.stream())
+            # by-products: bias gradient and the fp16 split of dgates
+            dgv = G.host(d_dg).astype(np.float64)
+            assert G.relerr(G.host(d_db), dgv.sum(0)) < 1e-5
+            ex = int(G.host(dge)[0])
+            rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / 2048.0) / 2.0 ** ex
+            assert np.abs(rec - dgv).max() <= max(np.abs(dgv).max() * 2.0 ** -20, 1e-12)
         else:
             G.call('ipavsr_lstm_bwd', d_dout.data_ptr(), d_whid.data_ptr(), G.ptr(d_peep), d_ci.data_ptr(), d_mask.data_ptr(),
                    d_gates.data_ptr(), d_cell.data_ptr(), d_dg.data_ptr(), G.ptr(d_dpeep), d_dci.data_ptr(), d_dhi.data_ptr(),

@@ -172,7 +172,7 @@ if 'lstm' in only:
             report('lstm_fwd_f16 N=%d H=%d tcgen05 (train saves)' % (N, H), ms, flops=2.0 * N * T * H * 4 * H, extra='  %.2f us/step' % (ms * 1e3 / T))
             ms = timeit(lambda: _lib.call('ipavsr_lstm_bwd_f16', dout.data_ptr(), whid.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4, 4 * H, peep.data_ptr(),
                                           ci.data_ptr(), mask.data_ptr(), gates.data_ptr(), cell.data_ptr(), dg.data_ptr(), dpeep.data_ptr(), dci.data_ptr(), dhi.data_ptr(),
-                                          N, T, H, ldh, 0, 5.0, 0, ws.data_ptr(), nbytes, st()), reps=5)
+                                          N, T, H, ldh, 0, 5.0, 0, None, None, None, None, ws.data_ptr(), nbytes, st()), reps=5)
             report('lstm_bwd_f16 N=%d H=%d tcgen05' % (N, H), ms, flops=2.0 * N * T * H * 4 * H, extra='  %.2f us/step' % (ms * 1e3 / T))
         del xw, out, hprev, gates, cell, dout, dg, ws
 if 'opt' in only:
