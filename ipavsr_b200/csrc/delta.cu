@@ -359,10 +359,14 @@ __global__ void __launch_bounds__(128) delta_bwd_col_kernel(const float* __restr
   }
 }
 
+// which Theta the constant table currently holds: ONE flag for every instantiation (a per-template static would let
+// <9,24> skip the upload after <4,24> had replaced the table)
+static int g_dbw_tab_theta = -1;
+
 template <int TH, int TMAX>
 static int launch_delta_bwd_col(const float* gy, int ldgy, float* gx, int ldgx, int N, int T, int F, int accumulate,
                                 cudaStream_t st) {
-  static int tab_theta = -1;
+  int& tab_theta = g_dbw_tab_theta;
   if (tab_theta != TH) {
     float tab[64];
     for (int d = 0; d < 64; ++d) {

@@ -626,3 +626,17 @@ def test_preprocessing_python_api_matches_reference_golden():
     seqs = np.array([[[1, 2, 3, 4, 5], [10, 12, 13, 14, 15], [300, 1, 23, 56, 22]]], dtype='float32')
     np.testing.assert_array_equal(S.append_delta_coeff(seqs[0], 1)[0],
                                   [1, 2, 3, 4, 5, 4.5, 5, 5, 5, 5, 72.5, -2.75, 2.5, 10.5, 1.75])
+
+
+def test_delta_bwd_alternating_windows():
+    """The register-column backward keeps its boundary weights in a constant table keyed by Theta: alternating window
+    sizes (and frame counts) must re-upload it every time it changes."""
+    rng = np.random.default_rng(3)
+    for theta, T in ((9, 20), (4, 20), (9, 20), (1, 33), (9, 40), (4, 40), (9, 40)):
+        N, F = 7, 10
+        gy = rng.normal(size=(N, T, 3 * F)).astype('float32')
+        want = ops.delta_bwd(gy, theta, np.float64)
+        d_gy, d_gx = G.dev(np.pad(gy.reshape(N * T, 3 * F), ((0, 0), (0, 2)))), G.zeros((N * T, 16))
+        G.call('ipavsr_delta_bwd', d_gy.data_ptr(), 3 * F + 2, d_gx.data_ptr(), 16, N, T, F, theta, 0, G.stream())
+        got = G.host(d_gx)[:, :F].reshape(N, T, F)
+        assert G.relerr(got, want) < 1e-5, (theta, T)
