@@ -177,7 +177,15 @@ def main():
         if rank != 0:
             return 0
         import torch
-        cores = torch.get_num_threads()
+        # all the host threads the BLAS behind NumPy can use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=ncpu)
+        except Exception:
+            pass
+        torch.set_num_threads(ncpu)
+        cores = ncpu
         n = min(args.cpu_sample, args.batch)
         steps = max(1, min(args.steps, 3))
         rate, spstep = cpu_reference_step_rate(n, steps, 1)
