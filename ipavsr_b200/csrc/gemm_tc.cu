@@ -919,6 +919,24 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
     if (x3 && acc_splits > splits) splits = acc_splits;
     if (splits > 64) splits = 64;
     if (splits < 1) splits = 1;
+    // Wave quantisation: when the product is split anyway, take the split count (from the minimum up to 3x it, at least
+    // 8 k-blocks each) whose CTA count fills whole waves of the machine best — 32 tiles x 5 splits = 160 CTAs would run
+    // as 1.08 waves of 148; 9 splits = 288 CTAs fill 1.95.
+    if (splits > 1) {
+      const int sms = sm_count();
+      int best = splits;
+      double best_eff = 0.0, min_eff = 0.0;
+      for (int s = splits; s <= 3 * splits && s <= 64 && num_kb / s >= 8; ++s) {
+        const int kps = (num_kb + s - 1) / s;
+        const int real = (num_kb + kps - 1) / kps;
+        const long long ctas = (long long)tiles * real;
+        const double eff = (double)ctas / (double)(((ctas + sms - 1) / sms) * sms);
+        if (s == splits) min_eff = eff;
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+      }
+      // every extra split costs another atomic epilogue over the whole output: only worth it for a big gain
+      if (best_eff > min_eff + 0.15) splits = best;
+    }
   }
   p.kb_per_split = (num_kb + splits - 1) / splits;
   splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;
