@@ -561,6 +561,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (rbase + rr < p.M)
                 *reinterpret_cast<float4*>(p.C + (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj) = o;
             }
+            if (p.C16hi != nullptr) {
+              // fp16 hi/lo split of the chunk under the static scale, from the same staging tile: 8 lanes cover 64
+              // contiguous bytes of a row in each array
+              const float sc = __int_as_float((127 + p.c16_exp) << 23);
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                const int rr = 4 * qq + (lane >> 3);
+                const float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + ((jj ^ (rr & 7)) << 2));
+                if (rbase + rr < p.M) {
+                  const float ov[4] = {o.x * sc, o.y * sc, o.z * sc, o.w * sc};
+                  __half h[4], l[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    h[j] = __float2half_rn(ov[j]);
+                    l[j] = __float2half_rn((ov[j] - __half2float(h[j])) * 2048.0f);
+                  }
+                  const size_t off = (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj;
+                  *reinterpret_cast<uint2*>(p.C16hi + off) = *reinterpret_cast<const uint2*>(h);
+                  *reinterpret_cast<uint2*>(p.C16lo + off) = *reinterpret_cast<const uint2*>(l);
+                }
+              }
+            }
           }
           __syncwarp();
         }
@@ -568,22 +590,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (p.amax != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) tile_max = fmaxf(tile_max, fabsf(v[j]));
-          }
-          if (p.C16hi != nullptr) {
-            const float sc = __int_as_float((127 + p.c16_exp) << 23);
-            const size_t off = (size_t)row * p.ldc + n0 + c0;
-#pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-              __half h[4], l[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float xs = v[j4 + j] * sc;
-                h[j] = __float2half_rn(xs);
-                l[j] = __float2half_rn((xs - __half2float(h[j])) * 2048.0f);
-              }
-              *reinterpret_cast<uint2*>(p.C16hi + off + j4) = *reinterpret_cast<const uint2*>(h);
-              *reinterpret_cast<uint2*>(p.C16lo + off + j4) = *reinterpret_cast<const uint2*>(l);
-            }
           }
           if (p.Chi != nullptr) {
             const size_t off = (size_t)row * p.ldc + n0 + c0;

@@ -306,9 +306,9 @@ class Engine(object):
         self._copy_stream = None
         self._prefetched = []
         self._c14 = None
-        # fp16 hi/lo of sigmoid/tanh outputs written by the GEMM epilogue itself (static scale 2^14).  Off by default: with
-        # the epilogue's row-per-thread store pattern the extra 8-byte stores cost more than the separate split pass saves.
-        self.epilogue_split = os.environ.get('IPAVSR_EPILOGUE_SPLIT', '0') == '1'
+        # fp16 hi/lo of sigmoid/tanh outputs written by the GEMM epilogue itself (static scale 2^14, coalesced through the
+        # epilogue's staging tile): saves the separate split pass over those activations (IPAVSR_EPILOGUE_SPLIT=0 disables)
+        self.epilogue_split = os.environ.get('IPAVSR_EPILOGUE_SPLIT', '1') == '1'
 
     # ------------------------------------------------------------------------------------------------
     # small helpers

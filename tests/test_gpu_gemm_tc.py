@@ -127,3 +127,31 @@ def test_f16x3_beats_single_pass_tf32():
     e3 = _run(4, 0, 0, 1040, 1000, 2000)
     e1 = _run(2, 0, 0, 1040, 1000, 2000)
     assert e3 < e1 / 50, (e3, e1)
+
+
+def test_f16x3_epilogue_emits_static_scale_split():
+    """C_hi / C_lo written by the epilogue (sigmoid output, static exponent 14) == ipavsr_f16_split of C with amax = 1."""
+    rng = np.random.default_rng(11)
+    M, N, K = 1040, 1000, 1200
+    A = rng.normal(size=(M, K)).astype('float32')
+    B = (rng.normal(size=(K, N)) / 30).astype('float32')
+    dA, dB = G.dev(A), G.dev(B)
+    ah, al = G.zeros((M, K), torch.float16), G.zeros((M, K), torch.float16)
+    bh, bl = G.zeros((K, N), torch.float16), G.zeros((K, N), torch.float16)
+    sc = G.zeros((4,))
+    G.call('ipavsr_f16_split', dA.data_ptr(), K, M, K, ah.data_ptr(), al.data_ptr(), K, sc.data_ptr(), sc.data_ptr() + 4, 0,
+           G.stream())
+    G.call('ipavsr_f16_split', dB.data_ptr(), N, K, N, bh.data_ptr(), bl.data_ptr(), N, sc.data_ptr() + 8, sc.data_ptr() + 12,
+           0, G.stream())
+    dC = G.zeros((M, N))
+    ch, cl = G.zeros((M, N), torch.float16), G.zeros((M, N), torch.float16)
+    G.call('ipavsr_gemm_f16x3', 0, 0, M, N, K, ah.data_ptr(), al.data_ptr(), K, sc.data_ptr() + 4, bh.data_ptr(),
+           bl.data_ptr(), N, sc.data_ptr() + 12, dC.data_ptr(), N, None, 1, 0, None, ch.data_ptr(), cl.data_ptr(), 14,
+           G.stream())
+    wh, wl = G.zeros((M, N), torch.float16), G.zeros((M, N), torch.float16)
+    one = G.dev(np.array([1.0, 0.0], 'float32'))
+    G.call('ipavsr_f16_split', dC.data_ptr(), N, M, N, wh.data_ptr(), wl.data_ptr(), N, one.data_ptr(), one.data_ptr() + 4, 1,
+           G.stream())
+    assert int(G.host(one).view(np.int32)[1]) == 14
+    np.testing.assert_array_equal(G.host(ch).view(np.uint16), G.host(wh).view(np.uint16))
+    np.testing.assert_array_equal(G.host(cl).view(np.uint16), G.host(wl).view(np.uint16))
