@@ -113,7 +113,9 @@ int ipavsr_colsum(const float* X, int ldx, float* out, int M, int N, int accumul
 
 /* ---- a2: DeltaLayer  (custom/layers.py:105-121 -> utils/signal.py:59-80) -------------------------------
  * x (N*T, F; ldx) -> y (N*T, 3F; ldy) = [x | delta | accel], window half-width theta, edge-replicated,
- * mask-agnostic.  exact=1 reproduces the reference's float64 intermediates with a float32 round per theta. */
+ * mask-agnostic.  exact=1 reproduces the reference's float64 intermediates with a float32 round per theta.
+ * Alignment padding of the output rows (columns 3F..ldy-1 when ldy - 3F < 8; likewise F..ldgx-1 of gx below) may be
+ * zero-filled: whole rows then leave as bulk copies.  Wider pitches (views into a larger matrix) are left untouched. */
 int ipavsr_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, int T, int F, int theta, int exact,
                      void* stream);
 /* gx (N*T, F) (+)= gy[:, :F] + D^T (gy[:, F:2F] + D^T gy[:, 2F:]) */

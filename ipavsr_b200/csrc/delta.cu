@@ -15,36 +15,12 @@
 // in DESIGN.md; HBM bound).
 #include <stdlib.h>
 #include "common.cuh"
+#include "delta_common.cuh"
 
 namespace ipavsr {
 
 constexpr int DELTA_THREADS = 256;
 constexpr int DELTA_RUN = 4;
-
-template <bool EXACT>
-__device__ __forceinline__ float delta_step(float acc, float diff, int th) {
-  if (EXACT) {
-    // The reference evaluates, in float64:  term = (theta*diff) / (2*theta*theta)  [= RN53(diff / (2 theta)), the
-    // numerator is exact],  s = RN53(acc + term),  acc = RN24(s)   (utils/signal.py:19-21).  Exact float32 ties of s
-    // are common (whenever 2*theta divides diff's mantissa), so the quotient has to be the correctly rounded one:
-    // for a power-of-two theta the product diff * (1/(2 theta)) is exact; otherwise one Markstein correction step
-    // (q = d*r; rem = fma(-q, c, d) exact; q' = fma(rem, r, q)) gives the correctly rounded quotient for these small
-    // integer divisors c.
-    // Power-of-two theta: the term diff / (2 theta) is exact in float32 and float32(float64(acc) + term) equals the single
-    // rounding of a float32 FMA (a float64 sum of two float32 values only rounds when they are > 2^29 apart, where no
-    // float32 rounding boundary is near), so those steps need no float64 arithmetic at all.
-    if ((th & (th - 1)) == 0) return fmaf(diff, 1.0f / (2.0f * (float)th), acc);
-    const double c = 2.0 * (double)th;
-    const double r = 1.0 / c;
-    const double d = (double)diff;
-    double q = d * r;
-    const double rem = fma(-q, c, d);
-    q = fma(rem, r, q);
-    return (float)((double)acc + q);
-  } else {
-    return fmaf(diff, 1.0f / (2.0f * (float)th), acc);
-  }
-}
 
 // src/dst: shared-memory tiles of one utterance, element (t,f) at [t*F + f]
 template <int TH, bool EXACT>
@@ -657,6 +633,11 @@ static int launch_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, i
   return IPAVSR_OK;
 }
 
+int delta_fwd_stream(const float* x, int ldx, float* y, int ldy, int N, int T, int F, int theta, int exact,
+                     cudaStream_t st);
+int delta_bwd_stream(const float* gy, int ldgy, float* gx, int ldgx, int N, int T, int F, int theta, int accumulate,
+                     cudaStream_t st);
+
 }  // namespace ipavsr
 
 using namespace ipavsr;
@@ -670,12 +651,17 @@ int ipavsr_delta_fwd(const float* x, int ldx, float* y, int ldy, int N, int T, i
   if (N == 0) return IPAVSR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool tiles_ok = (ldx % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ldy - 3 * F < 8 &&
                         ((size_t)DB_STAGES * T * ldx + (size_t)2 * T * ldy) * sizeof(float) <= 200 * 1024;
-  static int force_path = -1;   // IPAVSR_DELTA_PATH=bulk|col|general (benchmarking aid); default: automatic
+  static int force_path = -1;   // IPAVSR_DELTA_PATH=stream|bulk|col|general (benchmarking aid); default: automatic
   if (force_path < 0) {
     const char* e = getenv("IPAVSR_DELTA_PATH");
-    force_path = !e ? 0 : (e[0] == 'b' ? 1 : (e[0] == 'c' ? 2 : 3));
+    force_path = !e ? 0 : (e[0] == 's' ? 4 : (e[0] == 'b' ? 1 : (e[0] == 'c' ? 2 : 3)));
+  }
+  if (force_path == 0 || force_path == 4) {
+    // streaming kernel (delta_stream.cu): even F, T <= 48, Theta in {1,4,9} -- every shipped configuration
+    const int rc = delta_fwd_stream(x, ldx, y, ldy, N, T, F, theta, exact, st);
+    if (rc != -1) return rc;
   }
   // exact mode with a wide window is FP64-pipe bound: the register-resident column kernel is the faster one there
   const bool prefer_col = exact && theta >= 4 && T <= 48;
@@ -737,11 +723,16 @@ int ipavsr_delta_bwd(const float* gy, int ldgy, float* gx, int ldgx, int N, int 
   int blocks_needed = (N + upc - 1) / upc;
   int cap = sm_count() * 6;
   int grid = blocks_needed < cap ? blocks_needed : cap;
-  static int use_scatter = -1;          // IPAVSR_DELTA_BWD=scatter|tile selects the first-cut / shared-memory kernels
+  static int use_scatter = -1;          // IPAVSR_DELTA_BWD=scatter|tile|col selects the earlier kernels
   if (use_scatter < 0) {
     const char* e = getenv("IPAVSR_DELTA_BWD");
-    use_scatter = (e && e[0] == 's') ? 1 : ((e && e[0] == 't') ? 2 : 0);
+    use_scatter = (e && e[0] == 's') ? 1 : ((e && e[0] == 't') ? 2 : ((e && e[0] == 'c') ? 3 : 0));
   }
+  if (use_scatter == 0) {
+    const int rc = delta_bwd_stream(gy, ldgy, gx, ldgx, N, T, F, theta, accumulate, st);
+    if (rc != -1) return rc;
+  }
+  if (use_scatter == 3) use_scatter = 0;
   if (use_scatter == 0 && T <= 48 && (theta == 1 || theta == 4 || theta == 9)) {
     if (theta == 1) return dispatch_delta_bwd_col<1>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);
     if (theta == 4) return dispatch_delta_bwd_col<4>(gy, ldgy, gx, ldgx, N, T, F, accumulate, st);

@@ -58,7 +58,8 @@ def test_gemm_strided_views():
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('N,T,F,theta', [(2, 3, 5, 1), (26, 40, 50, 9), (7, 29, 90, 9), (5, 40, 30, 4), (3, 17, 50, 6),
                                          (1, 1, 4, 3), (300, 40, 50, 9), (4, 12, 51, 2), (1000, 40, 90, 9), (777, 29, 30, 4),
-                                         (130, 48, 50, 1), (70, 60, 20, 9)])
+                                         (130, 48, 50, 1), (70, 60, 20, 9), (9, 5, 50, 9), (4, 2, 30, 9), (3, 1, 50, 9),
+                                         (641, 40, 50, 9), (37, 24, 6, 4), (11, 25, 512, 9), (2, 40, 600, 9)])
 def test_delta_fwd_exact(N, T, F, theta):
     rng = np.random.default_rng(N + T + F + theta)
     x = rng.normal(size=(N, T, F)).astype('float32')
@@ -89,7 +90,9 @@ def test_delta_known_answers():
     np.testing.assert_array_equal(got[1, 2], [1, 1, 1, 1, 1, 0, 0, -49.5, 0, 0, 0, 0, -24.75, 0, 0])
 
 
-@pytest.mark.parametrize('N,T,F,theta', [(3, 11, 7, 2), (26, 40, 50, 9), (5, 1, 6, 4)])
+@pytest.mark.parametrize('N,T,F,theta', [(3, 11, 7, 2), (26, 40, 50, 9), (5, 1, 6, 4), (300, 40, 90, 9), (64, 29, 30, 4),
+                                         (9, 5, 50, 9), (33, 2, 30, 1), (12, 48, 50, 1), (7, 24, 6, 9), (641, 40, 50, 9),
+                                         (11, 25, 512, 9), (2, 40, 400, 9), (5, 60, 20, 9)])
 def test_delta_bwd(N, T, F, theta):
     rng = np.random.default_rng(9)
     g = rng.normal(size=(N, T, 3 * F)).astype('float32')
