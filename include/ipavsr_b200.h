@@ -184,6 +184,14 @@ int ipavsr_copy2d(const float* src, int lds, float* dst, int ldd, int M, int F, 
 /* SliceLayer(-1, axis=1): dst[n,:] = src[n*T + T-1, :] (fwd) ; scatter (bwd): dst[n*T+T-1,:] (+)= src[n,:] */
 int ipavsr_slice_last(const float* src, int lds, float* dst, int ldd, int N, int T, int F, int backward,
                       int accumulate, void* stream);
+/* ---- f1: device-side batch assembly  (utils/datagen.py:92-153 gen_lstm_batch_random, :219-229 gen_seq_batch_from_idx)
+ * The packed dataset `data` (total_frames, F; ldd) stays in HBM; utterance u occupies rows integral_lens[u] ..
+ * integral_lens[u] + seqlens[u] - 1 (utils/datagen.py:211-216 compute_integral_len).  For the N utterances idxs[i]:
+ *   X[i*T + t, :] = data[integral_lens[idxs[i]] + t, :] for t < seqlens[idxs[i]], zeros beyond   (seqlens <= T);
+ *   mask[i*T + t] = t < seqlens[idxs[i]]   (optional);   y_batch[i] = y[integral_lens[idxs[i]]]   (optional). */
+int ipavsr_batch_gather(const float* data, int ldd, const int64_t* integral_lens, const int32_t* seqlens,
+                        const int32_t* idxs, const uint8_t* y, float* X, int ldx, uint8_t* mask, uint8_t* y_batch,
+                        int N, int T, int F, void* stream);
 /* y = x * keep * scale (DropoutLayer with an explicit uint8 keep mask; same call is its backward) */
 int ipavsr_dropout(const float* x, int ldx, const uint8_t* keep, float* y, int ldy, int M, int F, float scale,
                    void* stream);

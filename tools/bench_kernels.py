@@ -10,7 +10,7 @@ import torch
 from ipavsr_b200 import _lib
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--only', default='delta,pre,gemm,lstm,opt')
+ap.add_argument('--only', default='delta,pre,batch,gemm,lstm,opt')
 ap.add_argument('--json', default=None)
 ap.add_argument('--reps', type=int, default=10)
 ap.add_argument('--frames', type=int, default=1048576)
@@ -105,6 +105,24 @@ if 'pre' in only:
     ms = timeit(fir)
     report('deltas_fir F=30 w=9 (float64 out)', ms, bytes_=(4.0 + 24.0) * F * frames)
     del x, y, xf, yf
+if 'batch' in only:
+    # padded (N, T, F) batch + mask gathered from a packed dataset resident in HBM
+    rng = np.random.default_rng(0)
+    U, Nb = 16384, 4096
+    for F in (1200, 90):
+        lens = rng.integers(20, T + 1, size=U)
+        integ = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.int64)
+        data = torch.randn(int(lens.sum()), F, device='cuda')
+        d_int, d_len = torch.from_numpy(integ).cuda(), torch.from_numpy(lens.astype(np.int32)).cuda()
+        idx = rng.permutation(U)[:Nb]
+        d_idx = torch.from_numpy(idx.astype(np.int32)).cuda()
+        X = torch.empty(Nb * T, F, device='cuda')
+        mask = torch.empty(Nb, T, dtype=torch.uint8, device='cuda')
+        ms = timeit(lambda: _lib.call('ipavsr_batch_gather', data.data_ptr(), F, d_int.data_ptr(), d_len.data_ptr(), d_idx.data_ptr(), None,
+                                      X.data_ptr(), F, mask.data_ptr(), None, Nb, T, F, st()))
+        report('batch_gather F=%d (%d utt x T=%d, mean len %.1f)' % (F, Nb, T, lens[idx].mean()), ms,
+               bytes_=4.0 * F * (float(lens[idx].sum()) + Nb * T) + Nb * T)
+        del data, X
 if 'gemm' in only:
     shapes = [('fc1 fwd', 0, 0, 20480, 2000, 1200), ('fc2 fwd', 0, 0, 20480, 1000, 2000), ('fc3 fwd', 0, 0, 20480, 500, 1000),
               ('bottleneck fwd', 0, 0, 20480, 50, 500), ('fc2 dgrad', 0, 1, 20480, 2000, 1000), ('fc1 wgrad', 1, 0, 1200, 2000, 20480),
