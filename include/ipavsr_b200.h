@@ -192,6 +192,13 @@ int ipavsr_slice_last(const float* src, int lds, float* dst, int ldd, int N, int
 int ipavsr_batch_gather(const float* data, int ldd, const int64_t* integral_lens, const int32_t* seqlens,
                         const int32_t* idxs, const uint8_t* y, float* X, int ldx, uint8_t* mask, uint8_t* y_batch,
                         int N, int T, int F, void* stream);
+/* ---- f2: evaluation on the device  (runners/2stream_dct.py:48-81 evaluate_model2; every runner's evaluate_model)
+ * probs (N*T, C; ldp): for utterance i, the argmax over the classes of each of its first seq_len = sum(mask[i,:]) frames
+ * (mask NULL: all T frames), a vote per class, pred[i] = the class with most votes; ties go to the lowest class index
+ * like np.argmax.  With targets y (N, uint8): confusion[y[i]*C + pred[i]] += 1 and *correct += (pred[i] == y[i]); both
+ * are ACCUMULATED (zero them first).  pred / confusion / correct are optional.  T = 1: sequence-level argmax. */
+int ipavsr_vote_eval(const float* probs, int ldp, const uint8_t* mask, const uint8_t* y, int N, int T, int C,
+                     int32_t* pred, int32_t* confusion, int32_t* correct, void* stream);
 /* y = x * keep * scale (DropoutLayer with an explicit uint8 keep mask; same call is its backward) */
 int ipavsr_dropout(const float* x, int ldx, const uint8_t* keep, float* y, int ldy, int M, int F, float scale,
                    void* stream);

@@ -50,6 +50,7 @@ _SIGS = {
     'ipavsr_copy2d': (I, [P, I, P, I, I, I, P, I, P]),
     'ipavsr_slice_last': (I, [P, I, P, I, I, I, I, I, I, P]),
     'ipavsr_batch_gather': (I, [P, I, P, P, P, P, P, I, P, P, I, I, I, P]),
+    'ipavsr_vote_eval': (I, [P, I, P, P, I, I, I, P, P, P, P]),
     'ipavsr_dropout': (I, [P, I, P, P, I, I, I, F, P]),
     'ipavsr_dropout_mask': (I, [P, U64, F, U64, U64, P]),
     'ipavsr_bn_stats': (I, [P, I, P, I, I, P]),

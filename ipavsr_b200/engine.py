@@ -842,6 +842,11 @@ class Engine(object):
             c0 += s.cols
         return out
 
+    def read_device(self, segs):
+        """Val -> contiguous (rows, cols) float32 torch tensor on the device."""
+        parts = [s.torch_view() for s in segs]
+        return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)).contiguous()
+
     def read(self, segs):
         """Val -> host ndarray (rows, cols)."""
         return np.concatenate([s.torch_view().detach().cpu().numpy() for s in segs], axis=1)

@@ -132,8 +132,12 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         dropout_masks = kw.get('dropout_masks')
         if not is_loss:
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
-            res = eng.read(out)
             lay = pred.layer
+            if kw.get('device_output'):
+                # the result stays in HBM as a torch tensor (on-device evaluation, utils/evaluate.py)
+                res = eng.read_device(out)
+                return res.reshape(run.N, run.T, -1) if len(lay.output_shape) == 3 else res
+            res = eng.read(out)
             if len(lay.output_shape) == 3:
                 res = res.reshape(run.N, run.T, -1)
             return res

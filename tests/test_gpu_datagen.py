@@ -12,6 +12,8 @@ import model_util as MU
 from ipavsr_b200 import layers as L
 from ipavsr_b200.function import function, tensor as T
 from ipavsr_b200.utils import datagen as DG
+from ipavsr_b200.custom.objectives import temporal_softmax_loss
+from ipavsr_b200.custom.updates import adam
 
 pytestmark = pytest.mark.gpu
 
@@ -108,3 +110,46 @@ def test_device_batches_feed_the_compiled_function():
     xb1 = dsets[1].gather(idxs, Tm)
     got = val_fn(xb0, mb, xb1, 3)
     np.testing.assert_array_equal(got, want)
+
+
+def test_training_from_the_device_generator_matches_host_batches():
+    """The runner loop (runners/2stream_dct.py:312-326) with gen_lstm_batch_random on the device: same costs, step by
+    step, as the reference generator's host batches under the same NumPy seed."""
+    rng = np.random.default_rng(5)
+    U = 17
+    seqlen = rng.integers(3, 12, size=U)
+    total = int(seqlen.sum())
+    dims = MU.build('adenet_v2', np.random.default_rng(21), fusiontype='sum')['dims']
+    streams = [rng.normal(size=(total, D)).astype('float32') for D in dims]
+    y = np.repeat(rng.integers(0, 7, size=U).astype('uint8'), seqlen)
+    integral = OD.compute_integral_len(seqlen)
+    Tm = int(seqlen.max())
+    costs = {}
+    for device_feed in (False, True):
+        spec = MU.build('adenet_v2', np.random.default_rng(21), fusiontype='sum')
+        net = spec['net']
+        ins = MU.input_layers(net)
+        targets, window = T.imatrix('targets'), T.iscalar('theta')
+        cost = temporal_softmax_loss(L.get_output(net, deterministic=False), targets, ins['mask'].input_var)
+        train = function([ins['input'].input_var, targets, ins['mask'].input_var, ins['dct'].input_var, window], cost,
+                         updates=adam(cost, L.get_all_params(net, trainable=True), learning_rate=1e-3))
+        np.random.seed(3)
+        out = []
+        if device_feed:
+            ds0, ds1 = DG.DeviceDataset(streams[0], seqlen, y=y), DG.DeviceDataset(streams[1], seqlen)
+            gen = DG.gen_lstm_batch_random(ds0, None, None, batchsize=6)
+            for _ in range(4):
+                X, yb, m, idx = next(gen)
+                yy = yb.reshape(-1, 1).expand(-1, m.shape[-1])
+                X2 = DG.gen_seq_batch_from_idx(ds1, idx, seqlen, integral, Tm)
+                out.append(float(train(X, yy, m, X2, 3)))
+        else:
+            sched = OD.batch_schedule(U, 6)
+            for _ in range(4):
+                idx = next(sched)
+                X, yb, m = OD.lstm_batch(streams[0], y, seqlen, idx)
+                yy = yb.reshape((-1, 1)).repeat(m.shape[-1], axis=-1)
+                X2 = OD.seq_batch_from_idx(streams[1], idx, seqlen, integral, Tm)
+                out.append(float(train(X, yy, m, X2, 3)))
+        costs[device_feed] = out
+    assert costs[True] == costs[False], costs

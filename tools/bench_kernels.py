@@ -123,6 +123,18 @@ if 'batch' in only:
         report('batch_gather F=%d (%d utt x T=%d, mean len %.1f)' % (F, Nb, T, lens[idx].mean()), ms,
                bytes_=4.0 * F * (float(lens[idx].sum()) + Nb * T) + Nb * T)
         del data, X
+if 'batch' in only:
+    # frame argmax -> per-utterance vote -> confusion matrix, probabilities resident in HBM
+    Nb, Cn = 4096, 26
+    probs = torch.rand(Nb * T, Cn, device='cuda')
+    lens_e = torch.randint(20, T + 1, (Nb,), device='cuda')
+    mask_e = (torch.arange(T, device='cuda')[None, :] < lens_e[:, None]).to(torch.uint8).contiguous()
+    y_e = torch.randint(0, Cn, (Nb,), device='cuda').to(torch.uint8)
+    pred = torch.empty(Nb, dtype=torch.int32, device='cuda')
+    conf, corr = torch.zeros(Cn, Cn, dtype=torch.int32, device='cuda'), torch.zeros(1, dtype=torch.int32, device='cuda')
+    ms = timeit(lambda: _lib.call('ipavsr_vote_eval', probs.data_ptr(), Cn, mask_e.data_ptr(), y_e.data_ptr(), Nb, T, Cn, pred.data_ptr(),
+                                  conf.data_ptr(), corr.data_ptr(), st()))
+    report('vote_eval %d utt x T=%d x C=%d' % (Nb, T, Cn), ms, bytes_=4.0 * Cn * float(lens_e.sum().item()) + Nb * T)
 if 'gemm' in only:
     shapes = [('fc1 fwd', 0, 0, 20480, 2000, 1200), ('fc2 fwd', 0, 0, 20480, 1000, 2000), ('fc3 fwd', 0, 0, 20480, 500, 1000),
               ('bottleneck fwd', 0, 0, 20480, 50, 500), ('fc2 dgrad', 0, 1, 20480, 2000, 1000), ('fc1 wgrad', 1, 0, 1200, 2000, 20480),
