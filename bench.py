@@ -156,7 +156,9 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--batch', type=int, default=512, help='utterances per GPU per step')
+    ap.add_argument('--batch', type=int, default=960,
+                    help='utterances per GPU per step (default 960 = 2 x 15 x 32: the tensor-core LSTM works on 32-utterance '
+                         'tiles, 15 of its 8-CTA clusters are co-resident, so multiples of 480 fill whole waves)')
     ap.add_argument('--mode', default=os.environ.get('IPAVSR_GEMM_MODE', 'f16x3'),
                     help='GEMM arithmetic: f16x3 (fp32-parity 3-product fp16 tensor cores, default) | tf32x3 (fp32-parity '
                          '3xTF32) | fp32 (CUDA cores) | tf32 (single pass)')
@@ -171,7 +173,7 @@ def main():
     config = {'workload': 'adenet_3stream train step (raw1200+diff1200+dct90 -> DBNF 2000-1000-500-50 -> delta(9) -> '
                           'LSTM-250 x3 -> concat -> BLSTM-250 -> softmax-26), T=40, variable lengths, Adam',
               'utterances_per_gpu': args.batch, 'global_batch': args.batch * world, 'frames': T_FRAMES,
-              'parallelism': 'dp%d' % world, 'timing': 'inputs (204 MB/step/GPU at 512 utt) larger than the 126 MB L2'}
+              'parallelism': 'dp%d' % world, 'timing': 'inputs (%d MB/step/GPU) larger than the 126 MB L2' % (args.batch * T_FRAMES * sum(STREAM_DIMS) * 4 // 1000000)}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -354,8 +356,9 @@ def main():
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, 'profiles', 'r01_dominant_kernel.json')))
-            if prof.get('mode') == args.mode and prof.get('shape') == [M, N, K]:
-                traffic = prof.get('dram_bytes_per_launch')
+            for ent in prof.get('entries', [prof]):
+                if ent.get('mode') == args.mode and ent.get('shape') == [M, N, K]:
+                    traffic = ent.get('dram_bytes_per_launch')
         except Exception:
             pass
         roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel: encoder fc1 GEMM %dx%dx%d (%s)' % (M, N, K, args.mode),

@@ -19,7 +19,8 @@ if 'delta' in which:
     for _ in range(2):
         _lib.call('ipavsr_delta_bwd', y.data_ptr(), 152, gx.data_ptr(), 56, N, T, F, 9, 0, st())
 if 'gemm' in which:
-    for (ta, tb, M, N, K) in ((0, 0, 20480, 2000, 1200), (1, 0, 1200, 2000, 20480)):
+    R = int(os.environ.get('IPAVSR_PROF_ROWS', '38400'))          # batch * T rows of the bench workload (960 x 40)
+    for (ta, tb, M, N, K) in ((0, 0, R, 2000, 1200), (1, 0, 1200, 2000, R)):
         lda, ldb = (M if ta else K), (K if tb else N)
         A = torch.randn(K if ta else M, lda, device='cuda'); B = torch.randn(N if tb else K, ldb, device='cuda')
         Cm = torch.empty(M, N, device='cuda'); bias = torch.zeros(N, device='cuda')

@@ -1,5 +1,5 @@
 """Per-entry-point device time of one bench training step (CUDA events around each C-ABI call).
-    python tools/profile_step.py [--mode tf32x3] [--batch 512]"""
+    python tools/profile_step.py [--mode tf32x3] [--batch 960]"""
 import argparse, os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -13,7 +13,7 @@ from ipavsr_b200.custom.updates import adam
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--mode', default='f16x3')
-ap.add_argument('--batch', type=int, default=512)
+ap.add_argument('--batch', type=int, default=960)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--by-shape', action='store_true', help='list GEMMs per shape')
 args = ap.parse_args()
