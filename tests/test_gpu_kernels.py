@@ -78,6 +78,41 @@ def test_delta_fwd_exact(N, T, F, theta):
     assert np.abs(got2 - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize('T,theta', [(40, 9), (29, 4)])
+def test_delta_wide_pitch_leaves_neighbours_untouched(T, theta):
+    """Outputs that are column slices of a wider matrix (row pitch well beyond the data): the streaming kernels must take
+    their register-store path and write nothing outside the [x | d | a] / g_x columns."""
+    rng = np.random.default_rng(T + theta)
+    N, F = 70, 50
+    ldx, ldy = 64, 3 * F + 18
+    x = rng.normal(size=(N, T, F)).astype('float32')
+    xp = rng.normal(size=(N * T, ldx)).astype('float32')
+    xp[:, :F] = x.reshape(N * T, F)
+    ys = rng.normal(size=(N * T, ldy)).astype('float32')
+    want = ops.delta_fwd(x, theta)
+    for exact in (1, 0):
+        dx, dy = G.dev(xp), G.dev(ys)
+        G.call('ipavsr_delta_fwd', dx.data_ptr(), ldx, dy.data_ptr(), ldy, N, T, F, theta, exact, G.stream())
+        got = G.host(dy)
+        np.testing.assert_array_equal(got[:, 3 * F:], ys[:, 3 * F:])
+        if exact:
+            np.testing.assert_array_equal(got[:, :3 * F].reshape(N, T, 3 * F), want)
+        else:
+            assert np.abs(got[:, :3 * F].reshape(N, T, 3 * F) - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+    g = rng.normal(size=(N, T, 3 * F)).astype('float32')
+    gp = rng.normal(size=(N * T, ldy)).astype('float32')
+    gp[:, :3 * F] = g.reshape(N * T, 3 * F)
+    wantg = ops.delta_bwd(g, theta, np.float64)
+    base = rng.normal(size=(N * T, ldx)).astype('float32')
+    for acc in (0, 1):
+        dg, dgx = G.dev(gp), G.dev(base)
+        G.call('ipavsr_delta_bwd', dg.data_ptr(), ldy, dgx.data_ptr(), ldx, N, T, F, theta, acc, G.stream())
+        got = G.host(dgx)
+        np.testing.assert_array_equal(got[:, F:], base[:, F:])
+        ref = wantg + (base[:, :F].reshape(N, T, F) if acc else 0)
+        assert G.relerr(got[:, :F].reshape(N, T, F), ref) < 2e-6
+
+
 def test_delta_known_answers():
     seqs = np.array([[[1, 2, 3, 4, 5], [10, 12, 13, 14, 15], [300, 1, 23, 56, 22]],
                      [[1, 1, 1, 1, 1], [1, 1, 100, 1, 1], [1, 1, 1, 1, 1]]], dtype='float32')
