@@ -152,4 +152,5 @@ def test_training_from_the_device_generator_matches_host_batches():
                 X2 = OD.seq_batch_from_idx(streams[1], idx, seqlen, integral, Tm)
                 out.append(float(train(X, yy, m, X2, 3)))
         costs[device_feed] = out
-    assert costs[True] == costs[False], costs
+    # same batches, same initial weights; split-K GEMMs accumulate with atomics, so two runs agree to rounding, not bit for bit
+    np.testing.assert_allclose(costs[True], costs[False], rtol=2e-5)
