@@ -1,6 +1,6 @@
 """One warm-up + one measured launch of each hot kernel at the bench shapes, for `ncu --set full` captures:
     ncu --set full --clock-control none --import-source on \
-        -k regex:'delta_(fwd|bwd)_col|gemm_tc_kernel|lstm_(fwd|bwd)_tc' -o gpurun_out/prof_r01 python tools/prof_targets.py"""
+        -k regex:'delta_stream|gemm_tc_kernel|lstm_(fwd|bwd)_tc' -o gpurun_out/prof_r01 python tools/prof_targets.py"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
