@@ -292,6 +292,15 @@ def main():
         return train(x0, dsets[1].gather(idx, T_FRAMES), dsets[2].gather(idx, T_FRAMES), dy, m0, THETA)
     ms_ds, _ = timed(step_dataset, args.steps, 3)
     del dsets
+    # SURVEY 8(d) quotes config 3 at 512 utterances per GPU: the same device-resident step at that batch, for comparison
+    # (16 LSTM tiles per launch = one full wave of the 15 co-resident clusters plus an almost empty one)
+    ms_512 = None
+    if args.batch != 512:
+        xs5, mask5, y5 = synth_batch(512, 2000 + rank)
+        d5 = [torch.from_numpy(x).cuda() for x in xs5]
+        m5, y5d = torch.from_numpy(mask5).cuda(), torch.from_numpy(y5).cuda()
+        ms_512, _ = timed(lambda: train(d5[0], d5[1], d5[2], y5d, m5, THETA), args.steps, 3)
+        del d5, xs5
     # forward-only (deterministic) pass of the same network: frames/s
     val_fn = function([v[0], v[1], v[2], mask_var, window], L.get_output(net, deterministic=True))
     ms_fwd, _ = timed(lambda: val_fn(dx[0], dx[1], dx[2], dmask, THETA), max(3, args.steps // 2), 3)
@@ -385,6 +394,9 @@ def main():
                 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu_baseline,
                 'model_tflops': flops_per_utt_train() * args.batch * world / (ms_dev * 1e-3) / 1e12,
                 'fwd_frames_per_s': fwd_frames, 'fwd_ms_per_batch': ms_fwd,
+                'batch_512': (None if ms_512 is None else
+                              {'value': 512 * world / (ms_512 * 1e-3), 'unit': 'utterances/s', 'ms_per_step': ms_512,
+                               'note': 'device-resident step at 512 utterances per GPU (SURVEY 8d batch)'}),
                 'device_dataset': {'value': args.batch * world / (ms_ds * 1e-3), 'unit': 'utterances/s',
                                    'ms_per_step': ms_ds,
                                    'note': 'batches gathered on the device from a packed dataset resident in HBM '
