@@ -266,6 +266,34 @@ int ipavsr_diff_image(const float* x, int ldx, float* y, int ldy, const int64_t*
 int ipavsr_deltas_fir(const float* x, int ldx, double* y, int ldy, const int64_t* offsets, int U, int F, int w,
                       int max_len, void* stream);
 
+/* ---- f3: the rest of utils/preprocessing.py on device -------------------------------- */
+/* zigzag (:280-338): order_host[i] (HOST buffer, rows*cols ints) = row-major index of the i-th element of the traversal
+ * (right, diagonal down-left, down, diagonal up-right, ...).  Pure index work, runs on the host.  Returns
+ * IPAVSR_ERR_ARG where the reference's walk raises IndexError (single-row / single-column shapes). */
+int ipavsr_zigzag_indices(int rows, int cols, int32_t* order_host);
+/* compute_dct_features (:417-462).  The reference takes scipy.fftpack.dct(X, norm='ortho') over the last axis of the
+ * (frames, D) matrix (:427) and keeps K columns of it (zigzag positions 1..K, or the K columns with the largest std /
+ * energy).  ipavsr_dct_basis fills basis (D, K; ldb) with those K type-2 orthonormal DCT basis vectors (cols[k] = the
+ * frequency index of column k, NULL = 0..K-1; evaluated in float64, rounded once); ipavsr_dct_project computes
+ * out (frames, K; ldo) = x (frames, D; ldx) * basis in float32 with FP32 accumulation. */
+int ipavsr_dct_basis(float* basis, int ldb, const int32_t* cols, int D, int K, void* stream);
+int ipavsr_dct_project(const float* x, int ldx, const float* basis, int ldb, float* out, int ldo, int64_t frames, int D,
+                       int K, void* stream);
+/* out[f, k] = x[f, idx[k]] and sums[c] = sum_f |x[f, c]| (float64): the column selection of the 'variance',
+ * 'rel_variance' and 'energy' methods (:434-459); the std of the other two comes from ipavsr_norm_featurewise_stats. */
+int ipavsr_gather_cols(const float* x, int ldx, const int32_t* idx, float* out, int ldo, int64_t frames, int K,
+                       void* stream);
+int ipavsr_col_abs_sum(const float* x, int ldx, double* sums, int64_t frames, int F, void* stream);
+/* reorder_data (:492-503): every frame is a d1 x d2 image flattened in Fortran ('f') or C ('c') order; to_c = 1 turns
+ * 'f' into 'c' (y[f, b*d2 + c] = x[f, b + d1*c]), to_c = 0 turns 'c' into 'f'.  Out of place (x != y). */
+int ipavsr_reorder(const float* x, int ldx, float* y, int ldy, int64_t frames, int d1, int d2, int to_c, void* stream);
+/* force_align (:607-660) / multistream_force_align (:672-712), mode 'fill': utterance u occupies input rows
+ * in_offsets[u] .. in_offsets[u+1]-1 and output rows out_offsets[u] .. out_offsets[u+1]-1 (U+1 prefix sums each, device);
+ * output row j of the utterance is input row j while j < its input length and the row fill_rows[u] (ABSOLUTE input row;
+ * NULL = the utterance's last frame) beyond.  out_rows = out_offsets[U]. */
+int ipavsr_align_fill(const float* x, int ldx, float* y, int ldy, const int64_t* in_offsets, const int64_t* out_offsets,
+                      const int64_t* fill_rows, int U, int D, int64_t out_rows, void* stream);
+
 /* profiling aid: when buf != NULL every tensor-core GEMM CTA writes 8 uint64 globaltimer stamps to
  * buf[8 * linear_cta_id ...] = {start, setup done, first stage landed, last MMA issued, accumulator ready, epilogue done} */
 int ipavsr_debug_gemm_timestamps(unsigned long long* buf);

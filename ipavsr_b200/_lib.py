@@ -67,6 +67,13 @@ _SIGS = {
     'ipavsr_seq_mean_sub': (I, [P, I, P, I, P, I, I, P]),
     'ipavsr_diff_image': (I, [P, I, P, I, P, I, I, P]),
     'ipavsr_deltas_fir': (I, [P, I, P, I, P, I, I, I, I, P]),
+    'ipavsr_zigzag_indices': (I, [I, I, P]),
+    'ipavsr_dct_basis': (I, [P, I, P, I, I, P]),
+    'ipavsr_dct_project': (I, [P, I, P, I, P, I, I64, I, I, P]),
+    'ipavsr_gather_cols': (I, [P, I, P, P, I, I64, I, P]),
+    'ipavsr_col_abs_sum': (I, [P, I, P, I64, I, P]),
+    'ipavsr_reorder': (I, [P, I, P, I, I64, I, I, I, P]),
+    'ipavsr_align_fill': (I, [P, I, P, I, P, P, P, I, I, I64, P]),
     'ipavsr_debug_gemm_timestamps': (I, [P]),
     'ipavsr_debug_lstm_timestamps': (I, [P]),
     'ipavsr_fill': (I, [P, U64, F, P]),

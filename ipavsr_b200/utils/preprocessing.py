@@ -119,3 +119,166 @@ def deltas(x, w=9):
     out = concat_first_second_deltas(np.ascontiguousarray(x.T, dtype=np.float32), [x.shape[1]], w)
     F = x.shape[0]
     return np.ascontiguousarray(out[:, F:2 * F].T)
+
+
+# ---- zigzag / compute_dct_features / reorder_data / force_align on the device (csrc/features.cu) ----
+
+def zigzag_order(rows, cols):
+    """Row-major positions of the `zigzag` traversal (`utils/preprocessing.py:280-338`), from the C-ABI's host-side
+    index walk.  IndexError where the reference's walk leaves the array."""
+    order = np.empty(int(rows) * int(cols), dtype=np.int32)
+    lib = _lib.load()
+    if lib.ipavsr_zigzag_indices(int(rows), int(cols), order.ctypes.data_as(C.c_void_p)) != 0:
+        raise IndexError(lib.ipavsr_last_error().decode())
+    return order
+
+
+def zigzag(X):
+    """`utils/preprocessing.py:280-338` (index work on the host; the device path of compute_dct_features never
+    materialises the traversal, it projects on the selected basis vectors only)."""
+    X = np.asarray(X)
+    return X.reshape(-1)[zigzag_order(*X.shape)]
+
+
+def fill_zigzag(shape):
+    """`utils/preprocessing.py:341-403`: the array whose zigzag traversal is 1..rows*cols."""
+    rows, cols = shape
+    out = np.zeros(rows * cols, dtype=np.float64)
+    out[zigzag_order(rows, cols)] = np.arange(1, rows * cols + 1)
+    return out.reshape(rows, cols)
+
+
+def _dct_project(x, cols):
+    """x (frames, D) on the device -> (frames, len(cols)) device tensor of the chosen DCT-II (ortho) coefficients."""
+    frames, D = x.shape
+    K = len(cols)
+    d_cols = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).cuda()
+    basis = torch.empty(D, K, dtype=torch.float32, device='cuda')
+    _lib.call('ipavsr_dct_basis', basis.data_ptr(), K, d_cols.data_ptr(), D, K, _st())
+    out = torch.empty(frames, K, dtype=torch.float32, device='cuda')
+    step = 65535 * 128
+    for f0 in range(0, frames, step):
+        n = min(step, frames - f0)
+        _lib.call('ipavsr_dct_project', x.data_ptr() + 4 * D * f0, D, basis.data_ptr(), K, out.data_ptr() + 4 * K * f0,
+                  K, n, D, K, _st())
+    return out
+
+
+def compute_dct_features(X, image_shape, no_coeff=30, method='zigzag'):
+    """`utils/preprocessing.py:417-462`.  The reference's DCT is scipy's 1-D type-2 orthonormal DCT over the flattened
+    image (:427); only the kept columns are computed here (zigzag positions 1..no_coeff), or — for the selection
+    methods — every AC column, whose std / energy then ranks them (argsort on the host over D-1 numbers)."""
+    if method not in ('zigzag', 'variance', 'rel_variance', 'energy'):
+        raise NotImplementedError("method not implemented, use only 'zigzag', 'variance', 'rel_variance")
+    x = _dev(X)
+    frames, D = x.shape
+    if method == 'zigzag':
+        if int(image_shape[0]) * int(image_shape[1]) != D:
+            raise ValueError('cannot reshape array of size %d into shape %r' % (D, tuple(image_shape)))
+        cols = zigzag_order(*image_shape)[1:no_coeff + 1]
+        return _dct_project(x, cols).cpu().numpy()
+    ac = _dct_project(x, np.arange(1, D))                     # X_dct[:, 1:]
+    F = D - 1
+    if method == 'energy':
+        score = torch.empty(F, dtype=torch.float64, device='cuda')
+        _lib.call('ipavsr_col_abs_sum', ac.data_ptr(), F, score.data_ptr(), frames, F, _st())
+    else:                                                     # the std of mean-removed columns is the std of the columns
+        mean = torch.empty(F, dtype=torch.float32, device='cuda')
+        score = torch.empty(F, dtype=torch.float32, device='cuda')
+        scratch = torch.empty(3 * F, dtype=torch.float64, device='cuda')
+        _lib.call('ipavsr_norm_featurewise_stats', ac.data_ptr(), F, mean.data_ptr(), score.data_ptr(),
+                  scratch.data_ptr(), frames, F, _st())
+    idxs = np.argsort(score.cpu().numpy())[::-1][:no_coeff]
+    d_idx = torch.from_numpy(np.ascontiguousarray(idxs, dtype=np.int32)).cuda()
+    K = len(idxs)
+    out = torch.empty(frames, K, dtype=torch.float32, device='cuda')
+    _lib.call('ipavsr_gather_cols', ac.data_ptr(), F, d_idx.data_ptr(), out.data_ptr(), K, frames, K, _st())
+    return out.cpu().numpy()
+
+
+def reorder_data(X, shape, orig_order='f', desired_order='c'):
+    """`utils/preprocessing.py:492-503`: per-frame (d1, d2) images from Fortran to C packing or back."""
+    d1, d2 = int(shape[0]), int(shape[1])
+    orig_order, desired_order = orig_order.lower(), desired_order.lower()
+    if orig_order not in 'fc' or desired_order not in 'fc':
+        raise ValueError("order must be 'f' or 'c'")
+    x = _dev(np.asarray(X).reshape(-1, d1 * d2))
+    if orig_order == desired_order:
+        return x.cpu().numpy()
+    y = torch.empty_like(x)
+    _lib.call('ipavsr_reorder', x.data_ptr(), d1 * d2, y.data_ptr(), d1 * d2, x.shape[0], d1, d2,
+              1 if desired_order == 'c' else 0, _st())
+    return y.cpu().numpy()
+
+
+def _align_plan(lens_in, lens_out, fill_rel):
+    """Offsets of the device gather and the same gather as a host row index (for the per-frame target vectors)."""
+    lens_in = np.asarray(lens_in, dtype=np.int64)
+    lens_out = np.asarray(lens_out, dtype=np.int64)
+    in_off = np.concatenate([[0], np.cumsum(lens_in)]).astype(np.int64)
+    out_off = np.concatenate([[0], np.cumsum(lens_out)]).astype(np.int64)
+    fill = in_off[:-1] + np.asarray(fill_rel, dtype=np.int64)
+    u = np.repeat(np.arange(len(lens_in)), lens_out)
+    j = np.arange(out_off[-1]) - out_off[u]
+    return in_off, out_off, fill, u, j
+
+
+def _align_gather(x, in_off, out_off, fill):
+    xd = _dev(x)
+    rows_in, D = xd.shape
+    if in_off[-1] != rows_in:
+        raise ValueError('sequence lengths sum to %d but the stream has %d frames' % (in_off[-1], rows_in))
+    out_rows = int(out_off[-1])
+    y = torch.empty(out_rows, D, dtype=torch.float32, device='cuda')
+    U = len(in_off) - 1
+    if U > 0 and out_rows > 0:
+        _lib.call('ipavsr_align_fill', xd.data_ptr(), D, y.data_ptr(), D, torch.from_numpy(in_off).cuda().data_ptr(),
+                  torch.from_numpy(out_off).cuda().data_ptr(), torch.from_numpy(fill).cuda().data_ptr(), U, D, out_rows,
+                  _st())
+        torch.cuda.current_stream().synchronize()          # the offset tensors above are temporaries
+    return y.cpu().numpy().astype(np.asarray(x).dtype, copy=False)
+
+
+def force_align(x1, x2, mode='fill'):
+    """`utils/preprocessing.py:607-660` (mode 'fill'; 'discard' is a TODO in the reference and returns empty streams
+    there).  Stream 2's fill frame is `x2[x2_curr_idx + l1 - 1]` (:652) — indexed with stream 1's length, i.e. a frame
+    of a LATER utterance whenever stream 1 is the longer one — reproduced, IndexError included; its fill target is the
+    utterance's own last target (:653).  The length vectors are updated in place and returned, like the reference."""
+    x1, t1, lens1 = x1
+    x2, t2, lens2 = x2
+    if mode != 'fill':
+        raise NotImplementedError("only mode='fill' exists in the reference")
+    l1 = np.asarray(lens1, dtype=np.int64).copy()
+    l2 = np.asarray(lens2, dtype=np.int64).copy()
+    lmax = np.maximum(l1, l2)
+    in1, out1, fill1, u1, j1 = _align_plan(l1, lmax, l1 - 1)
+    in2, out2, fill2, u2, j2 = _align_plan(l2, lmax, l1 - 1)                 # :652: l1, not l2
+    if len(l2) and np.any((lmax > l2) & (fill2 >= in2[-1])):
+        raise IndexError('index %d is out of bounds for axis 0 with size %d' % (fill2[(lmax > l2)].max(), in2[-1]))
+    n1 = _align_gather(x1, in1, out1, fill1)
+    n2 = _align_gather(x2, in2, out2, fill2)
+    t1, t2 = np.asarray(t1), np.asarray(t2)
+    nt1 = t1[in1[u1] + np.minimum(j1, l1[u1] - 1)]
+    nt2 = t2[in2[u2] + np.minimum(j2, l2[u2] - 1)]                          # :653: the utterance's own last target
+    for i in range(len(l1)):
+        lens1[i] = lmax[i]
+        lens2[i] = lmax[i]
+    return (n1, nt1, lens1), (n2, nt2, lens2)
+
+
+def multistream_force_align(orig_streams, mode='fill'):
+    """`utils/preprocessing.py:672-712`: every stream's utterance is extended to the longest stream's length with copies
+    of its own last frame and target; the length vectors are updated in place."""
+    if mode != 'fill':
+        raise NotImplementedError("only mode='fill' exists in the reference")
+    lens = [np.asarray(s[2], dtype=np.int64).copy() for s in orig_streams]
+    lmax = np.max(np.stack(lens), axis=0)
+    res = []
+    for (x, t, lvec), l in zip(orig_streams, lens):
+        in_off, out_off, fill, u, j = _align_plan(l, lmax, l - 1)
+        nx = _align_gather(x, in_off, out_off, fill)
+        nt = np.asarray(t)[in_off[u] + np.minimum(j, l[u] - 1)]
+        for i in range(len(l)):
+            lvec[i] = lmax[i]
+        res.append((nx, nt, lvec))
+    return res

@@ -158,3 +158,49 @@ def test_oracle_network_gradients_vs_finite_differences(name):
         assert abs(num - ana) < 1e-6 + 1e-4 * abs(num), (p.name, idx, num, ana)
         checked += 1
     assert checked == len(params)
+
+
+def test_zigzag_index_walk_of_the_c_abi_matches_the_reference_vectors():
+    """ipavsr_zigzag_indices is host-side index work: checked here without a GPU against the reference's own outputs."""
+    import ctypes as C
+    FG = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'features.npz'))
+    lib = _lib.load()
+    for r, c in FG['zigzag_shapes']:
+        want = FG['zigzag_%d_%d' % (r, c)]
+        order = np.empty(int(r) * int(c), dtype=np.int32)
+        rc = lib.ipavsr_zigzag_indices(int(r), int(c), order.ctypes.data_as(C.c_void_p))
+        if want[0] == -1:
+            assert rc == -1
+        else:
+            assert rc == 0
+            np.testing.assert_array_equal(order, want)
+
+
+def test_force_align_gather_plan_matches_the_reference_vectors(monkeypatch):
+    """The host half of force_align / multistream_force_align (offsets, fill rows, target gather, in-place length update)
+    with the device row gather replaced by its NumPy definition."""
+    from ipavsr_b200.utils import preprocessing as P
+    FG = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'features.npz'))
+
+    def gather(x, in_off, out_off, fill):
+        x = np.asarray(x)
+        u = np.repeat(np.arange(len(in_off) - 1), np.diff(out_off))
+        j = np.arange(out_off[-1]) - out_off[u]
+        return x[np.where(j < np.diff(in_off)[u], in_off[u] + j, fill[u])]
+
+    monkeypatch.setattr(P, '_align_gather', gather)
+    (na, nta, nl1), (nb, ntb, nl2) = P.force_align((FG['fa_a'], FG['fa_ta'], FG['fa_l1'].copy()),
+                                                   (FG['fa_b'], FG['fa_tb'], FG['fa_l2'].copy()))
+    for got, key in ((na, 'fa_out_a'), (nta, 'fa_out_ta'), (nl1, 'fa_out_l1'), (nb, 'fa_out_b'), (ntb, 'fa_out_tb'),
+                     (nl2, 'fa_out_l2')):
+        np.testing.assert_array_equal(got, FG[key])
+    res = P.multistream_force_align([(FG['fa_a'], FG['fa_ta'], FG['fa_l1'].copy()),
+                                     (FG['fa_b'], FG['fa_tb'], FG['fa_l2'].copy()),
+                                     (FG['ms_c'], FG['ms_tc'], FG['ms_l3'].copy())])
+    for j, (x, t, l) in enumerate(res):
+        np.testing.assert_array_equal(x, FG['ms_out_x%d' % j])
+        np.testing.assert_array_equal(t, FG['ms_out_t%d' % j])
+        np.testing.assert_array_equal(l, FG['ms_out_l%d' % j])
+    with pytest.raises(IndexError):
+        P.force_align((np.zeros((8, 4), 'float32'), np.zeros(8, 'uint8'), np.array([3, 5])),
+                      (np.zeros((5, 4), 'float32'), np.zeros(5, 'uint8'), np.array([3, 2])))

@@ -10,7 +10,7 @@ import torch
 from ipavsr_b200 import _lib
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--only', default='delta,pre,batch,gemm,lstm,opt')
+ap.add_argument('--only', default='delta,pre,feat,batch,gemm,lstm,opt')
 ap.add_argument('--json', default=None)
 ap.add_argument('--reps', type=int, default=10)
 ap.add_argument('--frames', type=int, default=1048576)
@@ -105,6 +105,36 @@ if 'pre' in only:
     ms = timeit(fir)
     report('deltas_fir F=30 w=9 (float64 out)', ms, bytes_=(4.0 + 24.0) * F * frames)
     del x, y, xf, yf
+if 'feat' in only:
+    # DCT projection on the zigzag basis vectors (4*D B read + 4*K B written per frame; 2*D*K flop per frame,
+    # FP32-pipe bound), per-frame image reorder (8*D B/frame), force-align row gather (8*D B per output frame)
+    from ipavsr_b200.utils import preprocessing as PP
+    frames, D, K = args.frames // 2, 1200, 30
+    x = torch.randn(frames, D, device='cuda')
+    cols = torch.from_numpy(PP.zigzag_order(30, 40)[1:K + 1].astype(np.int32)).cuda()
+    basis = torch.empty(D, K, device='cuda')
+    _lib.call('ipavsr_dct_basis', basis.data_ptr(), K, cols.data_ptr(), D, K, st())
+    out = torch.empty(frames, K, device='cuda')
+    ms = timeit(lambda: _lib.call('ipavsr_dct_project', x.data_ptr(), D, basis.data_ptr(), K, out.data_ptr(), K, frames, D, K, st()))
+    report('dct_project D=%d K=%d (%d frames)' % (D, K, frames), ms, bytes_=(4.0 * D + 4.0 * K) * frames, flops=2.0 * D * K * frames)
+    y = torch.empty_like(x)
+    ms = timeit(lambda: _lib.call('ipavsr_reorder', x.data_ptr(), D, y.data_ptr(), D, frames, 30, 40, 1, st()))
+    report('reorder_data 30x40 f->c (%d frames)' % frames, ms, bytes_=8.0 * D * frames)
+    U = frames // 32
+    rng = np.random.default_rng(0)
+    lin = rng.integers(12, 33, size=U).astype(np.int64)
+    lin[-1] += frames - int(lin.sum()) if int(lin.sum()) < frames else 0
+    lout = np.maximum(lin, rng.integers(12, 33, size=U))
+    in_off = torch.from_numpy(np.concatenate([[0], np.cumsum(lin)]).astype(np.int64)).cuda()
+    out_off_h = np.concatenate([[0], np.cumsum(lout)]).astype(np.int64)
+    out_off = torch.from_numpy(out_off_h).cuda()
+    rows_in, rows_out = int(lin.sum()), int(out_off_h[-1])
+    xa = torch.randn(rows_in, D, device='cuda')
+    ya = torch.empty(rows_out, D, device='cuda')
+    ms = timeit(lambda: _lib.call('ipavsr_align_fill', xa.data_ptr(), D, ya.data_ptr(), D, in_off.data_ptr(), out_off.data_ptr(), None, U, D, rows_out, st()))
+    report('align_fill D=%d (%d -> %d frames, %d utterances)' % (D, rows_in, rows_out, U), ms, bytes_=8.0 * D * rows_out)
+    del x, y, xa, ya, out
+
 if 'batch' in only:
     # padded (N, T, F) batch + mask gathered from a packed dataset resident in HBM
     rng = np.random.default_rng(0)
