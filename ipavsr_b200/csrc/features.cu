@@ -101,30 +101,140 @@ __global__ void __launch_bounds__(256) dct_project_kernel(const float* __restric
   }
 }
 
+// Aligned fast path of the same product (ldx, ldb, D multiples of 4 floats, 16-byte aligned bases): 128 threads per 128 x 32
+// tile, 8 frames (fg + 16 i) x 4 coefficients per thread (32 independent FFMA chains, 12 LDS.128 per 128 FFMA), operand
+// chunks brought in by 16-byte cp.async into a two-stage shared-memory ring (zero-filled past frames / D / K).
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(128, 4) dct_project_async_kernel(const float* __restrict__ x, int ldx,
+                                                                   const float* __restrict__ basis, int ldb,
+                                                                   float* __restrict__ out, int ldo, int64_t frames, int D,
+                                                                   int K) {
+  __shared__ __align__(16) float xs[2][DCT_TF * DCT_XP];
+  __shared__ __align__(16) float bs[2][DCT_DK * DCT_TK];
+  const int tid = threadIdx.x;
+  const int kb = blockIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.y * DCT_TF;
+  const int k0 = kb * DCT_TK;
+  const int cg = tid & 7, fg = tid >> 3;                   // fg 0..15
+
+  auto load_stage = [&](int st, int d0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {                          // 128 rows x 8 float4
+      const int idx = tid + 128 * j, row = idx >> 3, c4 = idx & 7;
+      const int64_t f = f0 + row;
+      const int d = d0 + 4 * c4;
+      const bool ok = f < frames && d < D;                 // D % 4 == 0: a float4 is inside or outside as a whole
+      cp_async16_zfill(&xs[st][row * DCT_XP + 4 * c4], ok ? (const void*)(x + f * ldx + d) : (const void*)x, ok ? 16 : 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {                          // 32 rows x 8 float4
+      const int idx = tid + 128 * j, row = idx >> 3, c4 = idx & 7;
+      const int d = d0 + row, k = k0 + 4 * c4;
+      int nb = (K - k) * 4;
+      nb = (d < D && nb > 0) ? (nb > 16 ? 16 : nb) : 0;
+      cp_async16_zfill(&bs[st][row * DCT_TK + 4 * c4], nb ? (const void*)(basis + (int64_t)d * ldb + k) : (const void*)basis, nb);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  const int nchunks = (D + DCT_DK - 1) / DCT_DK;
+  load_stage(0, 0);
+  for (int it = 0; it < nchunks; ++it) {
+    const int st = it & 1;
+    if (it + 1 < nchunks) {
+      load_stage(st ^ 1, (it + 1) * DCT_DK);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* xq = xs[st];
+    const float* bq = bs[st];
+#pragma unroll
+    for (int d4 = 0; d4 < DCT_DK / 4; ++d4) {
+      float4 xv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(&xq[(fg + 16 * i) * DCT_XP + 4 * d4]);
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) {
+        const float4 bv = *reinterpret_cast<const float4*>(&bq[(4 * d4 + dd) * DCT_TK + 4 * cg]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xe = dd == 0 ? xv[i].x : dd == 1 ? xv[i].y : dd == 2 ? xv[i].z : xv[i].w;
+          acc[i][0] = fmaf(xe, bv.x, acc[i][0]);
+          acc[i][1] = fmaf(xe, bv.y, acc[i][1]);
+          acc[i][2] = fmaf(xe, bv.z, acc[i][2]);
+          acc[i][3] = fmaf(xe, bv.w, acc[i][3]);
+        }
+      }
+    }
+    __syncthreads();                                       // this stage is refilled by the next iteration's load
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t f = f0 + fg + 16 * i;
+    if (f >= frames) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + 4 * cg + j;
+      if (k < K) out[f * ldo + k] = acc[i][j];
+    }
+  }
+}
+
 // reorder_data: out[f, j] = x[f, src(j)] with the per-frame (d1, d2) transpose.  to_c = 1 ('f' -> 'c'):
 // out[b*d2 + c] = x[b + d1*c];  to_c = 0 ('c' -> 'f'): out[b + d1*c] = x[b*d2 + c].  One frame per CTA iteration: the row is
 // read coalesced into shared memory and written coalesced in the new order.
 __global__ void __launch_bounds__(256) reorder_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy,
-                                                      int64_t frames, int d1, int d2, int to_c) {
-  extern __shared__ float row[];
+                                                      int64_t frames, int d1, int d2, int to_c, int R, int vec) {
+  extern __shared__ __align__(16) float rsm[];
   const int D = d1 * d2;
-  for (int64_t f = blockIdx.x; f < frames; f += gridDim.x) {
-    const float* xr = x + f * ldx;
-    for (int j = threadIdx.x; j < D; j += blockDim.x) row[j] = __ldg(xr + j);
-    __syncthreads();
-    float* yr = y + f * ldy;
-    for (int j = threadIdx.x; j < D; j += blockDim.x) {
-      int src;
-      if (to_c) {
-        const int b = j / d2, c = j - b * d2;
-        src = b + d1 * c;
-      } else {
-        const int c = j / d1, b = j - c * d1;
-        src = b * d2 + c;
+  int* src_tab = reinterpret_cast<int*>(rsm);               // D ints: source position of output position j (built once)
+  float* rows = rsm + ((D + 3) & ~3);                       // R frames
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    int src;
+    if (to_c) {
+      const int b = j / d2, c = j - b * d2;
+      src = b + d1 * c;
+    } else {
+      const int c = j / d1, b = j - c * d1;
+      src = b * d2 + c;
+    }
+    src_tab[j] = src;
+  }
+  const int64_t tiles = (frames + R - 1) / R;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int64_t f0 = t * R;
+    const int nf = (int)(frames - f0 < R ? frames - f0 : R);
+    __syncthreads();                                        // table ready / previous tile written out
+    if (vec) {
+      const int D4 = D >> 2;
+      for (int i = threadIdx.x; i < nf * D4; i += blockDim.x) {
+        const int f = i / D4, c = i - f * D4;
+        reinterpret_cast<float4*>(rows)[i] = __ldg(reinterpret_cast<const float4*>(x + (f0 + f) * ldx) + c);
       }
-      yr[j] = row[src];
+    } else {
+      for (int i = threadIdx.x; i < nf * D; i += blockDim.x) {
+        const int f = i / D, c = i - f * D;
+        rows[i] = __ldg(x + (f0 + f) * ldx + c);
+      }
     }
     __syncthreads();
+    for (int f = 0; f < nf; ++f) {
+      const float* rf = rows + f * D;
+      float* yr = y + (f0 + f) * ldy;
+      for (int j = threadIdx.x; j < D; j += blockDim.x) yr[j] = rf[src_tab[j]];
+    }
   }
 }
 
@@ -249,7 +359,11 @@ int ipavsr_dct_project(const float* x, int ldx, const float* basis, int ldb, flo
   const int64_t tiles = (frames + DCT_TF - 1) / DCT_TF;
   IPAVSR_CHECK_ARG(tiles <= 65535, "at most 65535 * 128 frames per call");
   dim3 grid((K + DCT_TK - 1) / DCT_TK, (unsigned)tiles);
-  dct_project_kernel<<<grid, 256, 0, S(stream)>>>(x, ldx, basis, ldb, out, ldo, frames, D, K);
+  const bool aligned = D % 4 == 0 && ldx % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)basis & 15) == 0;
+  if (aligned)
+    dct_project_async_kernel<<<grid, 128, 0, S(stream)>>>(x, ldx, basis, ldb, out, ldo, frames, D, K);
+  else
+    dct_project_kernel<<<grid, 256, 0, S(stream)>>>(x, ldx, basis, ldb, out, ldo, frames, D, K);
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }
@@ -258,14 +372,19 @@ int ipavsr_reorder(const float* x, int ldx, float* y, int ldy, int64_t frames, i
   IPAVSR_CHECK_ARG(x && y && x != y && frames >= 0 && d1 > 0 && d2 > 0, "x, y (distinct), d1, d2 > 0 are required");
   const int64_t D = (int64_t)d1 * d2;
   IPAVSR_CHECK_ARG(ldx >= D && ldy >= D, "leading dimensions are smaller than d1*d2");
-  IPAVSR_CHECK_ARG(D * 4 <= 200 * 1024, "d1*d2 floats must fit one CTA's shared memory (200 KB)");
+  IPAVSR_CHECK_ARG(D * 8 <= 200 * 1024, "d1*d2 floats (+ the index table) must fit one CTA's shared memory (200 KB)");
   if (frames == 0) return IPAVSR_OK;
-  const size_t smem = (size_t)D * 4;
+  const int64_t Dp = (D + 3) & ~(int64_t)3;
+  int R = (int)((40 * 1024 - Dp * 4) / (D * 4));            // ~40 KB per CTA: 5 CTAs per SM
+  if (R < 1) R = 1;
+  if (R > 16) R = 16;
+  const size_t smem = (size_t)(Dp + (int64_t)R * D) * 4;
   if (smem > 48 * 1024)
     IPAVSR_CUDA(cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t want = (int64_t)sm_count() * 8;
-  const unsigned grid = (unsigned)(frames < want ? frames : want);
-  reorder_kernel<<<grid, 256, smem, S(stream)>>>(x, ldx, y, ldy, frames, d1, d2, to_c ? 1 : 0);
+  const int vec = D % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0;
+  const int64_t tiles = (frames + R - 1) / R, want = (int64_t)sm_count() * 5;
+  const unsigned grid = (unsigned)(tiles < want ? tiles : want);
+  reorder_kernel<<<grid, 256, smem, S(stream)>>>(x, ldx, y, ldy, frames, d1, d2, to_c ? 1 : 0, R, vec);
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }

@@ -153,13 +153,14 @@ def _dct_project(x, cols):
     frames, D = x.shape
     K = len(cols)
     d_cols = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).cuda()
-    basis = torch.empty(D, K, dtype=torch.float32, device='cuda')
-    _lib.call('ipavsr_dct_basis', basis.data_ptr(), K, d_cols.data_ptr(), D, K, _st())
+    ldb = (K + 3) // 4 * 4                                   # 16-byte rows: the cp.async path of the kernel
+    basis = torch.empty(D, ldb, dtype=torch.float32, device='cuda')
+    _lib.call('ipavsr_dct_basis', basis.data_ptr(), ldb, d_cols.data_ptr(), D, K, _st())
     out = torch.empty(frames, K, dtype=torch.float32, device='cuda')
     step = 65535 * 128
     for f0 in range(0, frames, step):
         n = min(step, frames - f0)
-        _lib.call('ipavsr_dct_project', x.data_ptr() + 4 * D * f0, D, basis.data_ptr(), K, out.data_ptr() + 4 * K * f0,
+        _lib.call('ipavsr_dct_project', x.data_ptr() + 4 * D * f0, D, basis.data_ptr(), ldb, out.data_ptr() + 4 * K * f0,
                   K, n, D, K, _st())
     return out
 
@@ -232,10 +233,9 @@ def _align_gather(x, in_off, out_off, fill):
     y = torch.empty(out_rows, D, dtype=torch.float32, device='cuda')
     U = len(in_off) - 1
     if U > 0 and out_rows > 0:
-        _lib.call('ipavsr_align_fill', xd.data_ptr(), D, y.data_ptr(), D, torch.from_numpy(in_off).cuda().data_ptr(),
-                  torch.from_numpy(out_off).cuda().data_ptr(), torch.from_numpy(fill).cuda().data_ptr(), U, D, out_rows,
-                  _st())
-        torch.cuda.current_stream().synchronize()          # the offset tensors above are temporaries
+        d_in, d_out, d_fill = (torch.from_numpy(a).cuda() for a in (in_off, out_off, fill))    # alive until the copy back
+        _lib.call('ipavsr_align_fill', xd.data_ptr(), D, y.data_ptr(), D, d_in.data_ptr(), d_out.data_ptr(),
+                  d_fill.data_ptr(), U, D, out_rows, _st())
     return y.cpu().numpy().astype(np.asarray(x).dtype, copy=False)
 
 

@@ -112,11 +112,12 @@ if 'feat' in only:
     frames, D, K = args.frames // 2, 1200, 30
     x = torch.randn(frames, D, device='cuda')
     cols = torch.from_numpy(PP.zigzag_order(30, 40)[1:K + 1].astype(np.int32)).cuda()
-    basis = torch.empty(D, K, device='cuda')
-    _lib.call('ipavsr_dct_basis', basis.data_ptr(), K, cols.data_ptr(), D, K, st())
     out = torch.empty(frames, K, device='cuda')
-    ms = timeit(lambda: _lib.call('ipavsr_dct_project', x.data_ptr(), D, basis.data_ptr(), K, out.data_ptr(), K, frames, D, K, st()))
-    report('dct_project D=%d K=%d (%d frames)' % (D, K, frames), ms, bytes_=(4.0 * D + 4.0 * K) * frames, flops=2.0 * D * K * frames)
+    for ldb, tag in ((32, 'cp.async path'), (K, 'generic path')):
+        basis = torch.empty(D, ldb, device='cuda')
+        _lib.call('ipavsr_dct_basis', basis.data_ptr(), ldb, cols.data_ptr(), D, K, st())
+        ms = timeit(lambda: _lib.call('ipavsr_dct_project', x.data_ptr(), D, basis.data_ptr(), ldb, out.data_ptr(), K, frames, D, K, st()))
+        report('dct_project D=%d K=%d %s (%d frames)' % (D, K, tag, frames), ms, bytes_=(4.0 * D + 4.0 * K) * frames, flops=2.0 * D * K * frames)
     y = torch.empty_like(x)
     ms = timeit(lambda: _lib.call('ipavsr_reorder', x.data_ptr(), D, y.data_ptr(), D, frames, 30, 40, 1, st()))
     report('reorder_data 30x40 f->c (%d frames)' % frames, ms, bytes_=8.0 * D * frames)
