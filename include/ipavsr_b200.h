@@ -237,6 +237,18 @@ int ipavsr_categorical_crossentropy(const float* probs, int ldp, const int32_t* 
                                     float* dlogits, int lddl, int M, int C, float inv_norm,
                                     const float* count_dev, void* stream);
 
+/* ---- f4: auto-encoder fine-tuning objective (avletters/trimodal.py:41-89: nolearn NeuralNet with
+ * objective_loss_function=squared_error, objective_l2=0.005; oulu/bimodal.py:34-82) ---------------------------------- */
+/* loss_sum[0] += sum_{r,c} (pred - target)^2;  dpred (optional) = 2 * grad_scale * (pred - target)   (grad_scale = 1/(M_global*F)
+ * for lasagne.objectives.squared_error(...).mean()) */
+int ipavsr_squared_error(const float* pred, int ldp, const float* target, int ldt, float* loss_sum, float* dpred, int lddp,
+                         int64_t M, int F, float grad_scale, void* stream);
+/* lasagne.regularization.regularize_network_params(net, l2) * coefficient over the flat parameter arena: with
+ * c = seg_coef[seg_id[i / 256]] (0 for non-regularizable tensors: biases, initial states) g[i] += 2 c p[i] (g optional)
+ * and loss_sum[0] += loss_scale * sum_i c p[i]^2. */
+int ipavsr_l2_penalty(const float* p, float* g, uint64_t n, const float* seg_coef, const int32_t* seg_id, float* loss_sum,
+                      float loss_scale, void* stream);
+
 /* ---- a9: update rules over a flat parameter arena ----------------------------------------------------- */
 /* One fused multi-tensor step over n floats.  lr_scale (device, n/segment granularity) is NULL for a single
  * learning rate, else `seg_lr` is a device array giving the per-parameter-tensor learning rate and `seg_id`

@@ -60,6 +60,8 @@ _SIGS = {
     'ipavsr_softmax': (I, [P, I, P, I, I, I, P]),
     'ipavsr_temporal_softmax_loss': (I, [P, I, P, P, P, P, I, I, I, F, P, P]),
     'ipavsr_categorical_crossentropy': (I, [P, I, P, P, P, I, I, I, F, P, P]),
+    'ipavsr_squared_error': (I, [P, I, P, I, P, P, I, I64, I, F, P]),
+    'ipavsr_l2_penalty': (I, [P, P, U64, P, P, P, F, P]),
     'ipavsr_optim_step': (I, [I, P, P, P, P, U64, F, P, P, F, F, F, F, F, P]),
     'ipavsr_norm_samplewise': (I, [P, I, P, I, I64, I, P]),
     'ipavsr_norm_featurewise_stats': (I, [P, I, P, P, P, I64, I, P]),

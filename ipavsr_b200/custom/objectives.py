@@ -13,3 +13,10 @@ def categorical_crossentropy(predictions, targets):
     """Element-wise `-log p[n, y_n]`; wrap in `function.tensor.mean(...)` as the runners do
     (`avletters/trimodal.py:327`)."""
     return LossExpr('categorical_crossentropy_elemwise', predictions, targets, None)
+
+
+def squared_error(a, b):
+    """Element-wise `(a - b)**2` (lasagne.objectives.squared_error, the `objective_loss_function` of the auto-encoder
+    fine-tuning nets, `avletters/trimodal.py:81`); wrap in `function.tensor.mean(...)`; an L2 penalty is added with
+    `+ coefficient * ipavsr_b200.regularization.regularize_network_params(net, l2)`."""
+    return LossExpr('squared_error_elemwise', a, b, None)

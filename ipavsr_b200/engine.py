@@ -879,16 +879,19 @@ class Engine(object):
         for a, b in zip(segs, dst):
             _lib.call('ipavsr_copy2d', a.ptr, a.ld, b.ptr, b.ld, a.rows, a.cols, None, 1, self.stream)
 
-    def backward(self, run, dlogits):
-        """dlogits: DevMat gradient w.r.t. the pre-softmax logits of the output Dense.  Writes the gradient arena."""
+    def backward(self, run, dlogits, softmax_head=True):
+        """dlogits: DevMat gradient w.r.t. the pre-softmax logits of the output Dense (softmax_head) or w.r.t. the output of
+        a non-softmax output Dense (regression nets: auto-encoder fine-tuning).  Writes the gradient arena."""
         lib, st, ar = self.lib, self.stream, self.arena
         N, T = run.N, run.T
         G = lambda key: ar.mat(key, 'grad')
         head = self.out
         while isinstance(head, L.ReshapeLayer):
             head = head.input_layer
-        if not (isinstance(head, L.DenseLayer) and head.nonlinearity.name == 'softmax'):
+        if softmax_head and not (isinstance(head, L.DenseLayer) and head.nonlinearity.name == 'softmax'):
             raise ValueError('the network output must be a softmax DenseLayer to train')
+        if not softmax_head and not (isinstance(head, L.DenseLayer) and head.nonlinearity.name != 'softmax'):
+            raise ValueError('a squared-error objective needs a non-softmax DenseLayer output')
         run.grads[head] = ([dlogits], True)
         # number of not-yet-processed consumers of every layer: when it reaches zero the layer's gradient is final and
         # an LSTM recurrence can be launched ahead of the walk on a side stream
@@ -1131,14 +1134,84 @@ class Engine(object):
             ar.grad[ar.tail + 1: ar.tail + 2].fill_(float(n_glob))
             _lib.call('ipavsr_categorical_crossentropy', p.ptr, p.ld, yd.data_ptr(), tail, dlogits.ptr, dlogits.ld,
                       p.rows, p.cols, 1.0 / n_glob, None, st)
+        elif loss == 'squared_error':
+            # T.mean(squared_error(pred, target)): mean over every element of the GLOBAL batch; dlogits is d/d(output)
+            td = self._target_matrix(y, p)
+            n_glob = p.rows * p.cols * (self.world[1] if self.world is not None else 1)
+            ar.grad[ar.tail + 1: ar.tail + 2].fill_(float(n_glob))
+            _lib.call('ipavsr_squared_error', p.ptr, p.ld, td.ptr, td.ld, tail, dlogits.ptr, dlogits.ld, p.rows, p.cols,
+                      1.0 / n_glob, st)
+            self.backward(run, dlogits, softmax_head=False)
+            return
         else:
             raise ValueError('unknown loss %r' % (loss,))
         self.backward(run, dlogits)
 
-    def loss_only(self, probs, loss, y, mask):
+    def _target_matrix(self, y, p):
+        """Regression targets (rows, F) or (N, T, F), host or device -> device matrix with the rows of the prediction."""
+        if isinstance(y, DevMat):
+            return y
+        t = y if isinstance(y, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(y).astype(np.float32, copy=False)))
+        if t.shape[-1] != p.cols or t.numel() != p.rows * p.cols:
+            raise ValueError('targets of shape %r do not match predictions (%d, %d)' % (tuple(t.shape), p.rows, p.cols))
+        return self._upload(t.reshape(p.rows, 1, p.cols), 'float')
+
+    def _l2_tables(self, coef):
+        """Per-tensor penalty coefficients over the arena: `coef` for tensors whose parameters are all regularizable."""
+        ar = self.arena
+        if getattr(self, '_l2_cache', None) is not None and self._l2_cache[0] == coef:
+            return self._l2_cache[1], self._l2_cache[2]
+        reg = {}
+        for prm in L.get_all_params(self.out):
+            if prm not in ar.bind or ar.bind[prm][1] == 'aux':
+                continue
+            k = ar.tensor_of(prm)
+            reg[k] = reg.get(k, True) and ('regularizable' in prm.tags)
+        cs = np.zeros(len(ar.order) + 1, dtype=np.float32)
+        for i, k in enumerate(ar.order):
+            cs[i] = coef if reg.get(k, False) else 0.0
+        ids = np.zeros(ar.n // SEG + 1, dtype=np.int32)
+        ids[:len(ar.seg_host)] = ar.seg_host
+        ids[len(ar.seg_host):] = len(ar.order)            # the loss tail: coefficient 0
+        seg_c = torch.from_numpy(cs).to(self.device)
+        seg_i = torch.from_numpy(ids).to(self.device)
+        self._l2_cache = (coef, seg_c, seg_i)
+        return seg_c, seg_i
+
+    def l2_penalty(self, coef, grads=True, loss_buf=None, count=None):
+        """`+ coef * regularize_network_params(net, l2)`: adds 2 coef W to the gradients of the regularizable tensors and
+        coef * sum W^2 to the loss (scaled by the loss normaliser, which read_loss divides by).  Data-parallel: rank 0 alone
+        adds it, the gradient all-reduce (SUM) distributes it."""
+        if self.world is not None and self.world[0] != 0:
+            return
+        ar = self.arena
+        seg_c, seg_i = self._l2_tables(float(coef))
+        if count is None:
+            count = float(ar.grad[ar.tail + 1].item()) if loss_buf is None else 1.0
+        tail = ar.grad.data_ptr() + 4 * ar.tail if loss_buf is None else loss_buf
+        _lib.call('ipavsr_l2_penalty', ar.flat.data_ptr(), ar.grad.data_ptr() if grads else None, ar.n, seg_c.data_ptr(),
+                  seg_i.data_ptr(), tail, float(count), self.stream)
+
+    def loss_only(self, probs, loss, y, mask, l2=0.0):
         st = self.stream
         p = probs[0]
         buf = torch.zeros(4, dtype=torch.float32, device=self.device)
+        if loss == 'squared_error':
+            td = self._target_matrix(y, p)
+            _lib.call('ipavsr_squared_error', p.ptr, p.ld, td.ptr, td.ld, buf.data_ptr(), None, 0, p.rows, p.cols, 1.0, st)
+            both = torch.stack([buf[0], torch.tensor(float(p.rows * p.cols), dtype=torch.float32, device=self.device)])
+            if self.world is not None:
+                torch.distributed.all_reduce(both, group=self.world[2])
+            h = both.cpu().numpy()
+            val = np.float32(h[0] / h[1])
+            if l2:
+                pen = torch.zeros(1, dtype=torch.float32, device=self.device)
+                seg_c, seg_i = self._l2_tables(float(l2))
+                _lib.call('ipavsr_l2_penalty', self.arena.flat.data_ptr(), None, self.arena.n, seg_c.data_ptr(),
+                          seg_i.data_ptr(), pen.data_ptr(), 1.0, st)
+                val = np.float32(val + np.float32(pen.item()))
+            return val
         yd = self._upload(y, 'int')
         if loss == 'temporal_softmax':
             md = self._upload(mask, 'mask')

@@ -42,15 +42,28 @@ class _TensorNamespace(object):
     def mean(x):
         if isinstance(x, LossExpr) and x.kind == 'categorical_crossentropy_elemwise':
             return LossExpr('categorical_crossentropy', x.pred, x.targets, None)
-        raise TypeError('T.mean is only defined on categorical_crossentropy(...) here')
+        if isinstance(x, LossExpr) and x.kind == 'squared_error_elemwise':
+            return LossExpr('squared_error', x.pred, x.targets, None)
+        raise TypeError('T.mean is only defined on categorical_crossentropy(...) / squared_error(...) here')
 
 
 tensor = _TensorNamespace()
 
 
 class LossExpr(object):
-    def __init__(self, kind, pred, targets, mask):
-        self.kind, self.pred, self.targets, self.mask = kind, pred, targets, mask
+    def __init__(self, kind, pred, targets, mask, l2=0.0):
+        self.kind, self.pred, self.targets, self.mask, self.l2 = kind, pred, targets, mask, float(l2)
+
+    def __add__(self, other):
+        """`loss + coefficient * regularize_network_params(net, l2)` (nolearn's objective, `avletters/trimodal.py:87`)."""
+        from .regularization import Penalty
+        if not isinstance(other, Penalty):
+            return NotImplemented
+        if other.layer is not self.pred.layer:
+            raise ValueError('the penalty must be taken over the network the loss is computed on')
+        return LossExpr(self.kind, self.pred, self.targets, self.mask, self.l2 + other.coefficient)
+
+    __radd__ = __add__
 
 
 class UpdateSpec(object):
@@ -113,10 +126,11 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
             raise ValueError('the loss mask must be the network mask input')
     is_loss = isinstance(outputs, LossExpr)
     train = updates is not None
-    loss_name = {'temporal_softmax': 'temporal_softmax',
-                 'categorical_crossentropy': 'categorical_crossentropy'}.get(outputs.kind) if is_loss else None
+    loss_name = {'temporal_softmax': 'temporal_softmax', 'categorical_crossentropy': 'categorical_crossentropy',
+                 'squared_error': 'squared_error'}.get(outputs.kind) if is_loss else None
     if is_loss and loss_name is None:
-        raise TypeError('wrap categorical_crossentropy(...) in T.mean(...)')
+        raise TypeError('wrap categorical_crossentropy(...) / squared_error(...) in T.mean(...)')
+    l2 = outputs.l2 if is_loss else 0.0
 
     def fn(*args, **kw):
         if len(args) != len(slots):
@@ -144,11 +158,13 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         mask = feed[mask_layer] if mask_layer is not None else None
         if not train:
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
-            return eng.loss_only(out, loss_name, y, mask)
+            return eng.loss_only(out, loss_name, y, mask, l2=l2)
         run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks)
         eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
                               count=float(np.asarray(mask).sum()) if (mask is not None and not hasattr(mask, 'is_cuda'))
                               else None)
+        if l2:
+            eng.l2_penalty(l2)
         eng.allreduce_grads()
         u = updates
         eng.optim_step(u.kind, _lr_value(u.lr) if u.lr is not None else 0.0, params=u.params, lr_map=u.lr_map, **u.hp)

@@ -175,14 +175,24 @@ class OracleNet(object):
 
     # convenience: loss + grads in get_all_params(trainable=True) order
     def loss_and_grads(self, inputs, window, y, mask, loss='temporal_softmax', deterministic=False,
-                       dropout_masks=None, update_bn=True):
+                       dropout_masks=None, update_bn=True, l2=0.0):
         out = self.forward(inputs, window, deterministic, dropout_masks, update_bn)
         if loss == 'temporal_softmax':
             val, dout = ops.temporal_softmax_loss(out, y, mask, self.dt)
         elif loss == 'categorical_crossentropy':
             val, dout = ops.categorical_crossentropy_mean(out, y, self.dt)
+        elif loss == 'squared_error':
+            val, dout = ops.squared_error_mean(out, y, self.dt)
         else:
             raise ValueError(loss)
         grads = self.backward(dout)
         params = self.L.get_all_params(self.out, trainable=True)
+        if l2:
+            # + l2 * lasagne.regularization.regularize_network_params(net, l2): sum of squares of the regularizable
+            # parameters (nolearn objective_l2, avletters/trimodal.py:87)
+            for p in self.L.get_all_params(self.out, regularizable=True):
+                w = np.asarray(p.get_value(), self.dt)
+                val = self.dt(val + self.dt(l2) * (w * w).sum())
+                if p in grads:
+                    grads[p] = grads[p] + 2 * self.dt(l2) * w.reshape(np.asarray(grads[p]).shape)
         return val, out, [np.asarray(grads[p], self.dt).reshape(p.shape) for p in params]

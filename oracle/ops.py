@@ -328,6 +328,14 @@ def categorical_crossentropy_mean(probs, y, dt=np.float32):
     return dt(loss), dp
 
 
+def squared_error_mean(pred, target, dt=np.float32):
+    """T.mean(lasagne.objectives.squared_error(pred, target)) — nolearn's regression objective
+    (`avletters/trimodal.py:81`): mean over every element; returns (loss, d loss / d pred)."""
+    p = np.asarray(pred, dt)
+    d = p - np.asarray(target, dt).reshape(p.shape)
+    return dt((d * d).mean()), (2.0 / d.size) * d
+
+
 # ---------------------------------------------------------------------------------------------------
 # a9  update rules (custom/updates.py:35-99; Lasagne adam/adadelta/sgd/momentum; SURVEY A.7)
 # ---------------------------------------------------------------------------------------------------

@@ -204,3 +204,50 @@ def test_force_align_gather_plan_matches_the_reference_vectors(monkeypatch):
     with pytest.raises(IndexError):
         P.force_align((np.zeros((8, 4), 'float32'), np.zeros(8, 'uint8'), np.array([3, 5])),
                       (np.zeros((5, 4), 'float32'), np.zeros(5, 'uint8'), np.array([3, 2])))
+
+
+def test_nolearn_train_split_is_the_first_unshuffled_fold():
+    from sklearn.model_selection import KFold
+    from ipavsr_b200.custom.nolearn_net import train_split
+    for n in (5, 7, 100, 103, 700, 1001):
+        tr_want, va_want = next(iter(KFold(5).split(np.zeros((n, 1)))))
+        tr, va = train_split(n, 0.2)
+        np.testing.assert_array_equal(tr, tr_want)
+        np.testing.assert_array_equal(va, va_want)
+
+
+def test_squared_error_l2_objective_expression_and_oracle_gradients():
+    """`T.mean(squared_error(out, y)) + 0.005 * regularize_network_params(net, l2)` builds one loss expression; the oracle's
+    value and gradients of that objective agree with central finite differences (float64)."""
+    from ipavsr_b200.function import tensor as T, LossExpr
+    from ipavsr_b200.custom.objectives import squared_error
+    from ipavsr_b200.regularization import regularize_network_params, l2
+    from oracle.net import OracleNet
+    rng = np.random.default_rng(0)
+    x = T.tensor3('x')
+    l_in = L.InputLayer((None, None, 6), x, name='input')
+    l = L.ReshapeLayer(l_in, (-1, 6))
+    l = L.DenseLayer(l, 4, W=rng.normal(size=(6, 4)).astype('float32'), b=rng.normal(size=4).astype('float32'),
+                     nonlinearity=nl.sigmoid, name='l1')
+    out = L.DenseLayer(l, 6, W=rng.normal(size=(4, 6)).astype('float32'), b=rng.normal(size=6).astype('float32'),
+                       nonlinearity=nl.linear, name='output')
+    y = T.matrix('y')
+    loss = T.mean(squared_error(L.get_output(out), y)) + 0.005 * regularize_network_params(out, l2)
+    assert isinstance(loss, LossExpr) and loss.kind == 'squared_error' and abs(loss.l2 - 0.005) < 1e-12
+    X = rng.normal(size=(5, 1, 6))
+    params = L.get_all_params(out, trainable=True)
+
+    def value():
+        return float(OracleNet(out, np.float64).loss_and_grads({'input': X}, 0, X.reshape(5, 6), None, 'squared_error',
+                                                               l2=0.005)[0])
+
+    _, _, grads = OracleNet(out, np.float64).loss_and_grads({'input': X}, 0, X.reshape(5, 6), None, 'squared_error', l2=0.005)
+    for p, g in zip(params, grads):
+        w = p.get_value().astype(np.float64)
+        idx = tuple(rng.integers(0, s) for s in w.shape)
+        eps = 1e-3
+        keep = p.get_value().copy()
+        wp = keep.copy(); wp[idx] += eps; p.set_value(wp); up = value()
+        wm = keep.copy(); wm[idx] -= eps; p.set_value(wm); dn = value()
+        p.set_value(keep)
+        assert abs((up - dn) / (2 * eps) - g[idx]) <= 2e-3 * max(abs(g[idx]), 1e-3), p.name
