@@ -9,3 +9,14 @@ def create_model(s1_ae, s2_ae, s3_ae, s1_shape, s1_var, s2_shape, s2_var, s3_sha
     return _nstream.build([s1_ae, s2_ae, s3_ae], [s1_shape, s2_shape, s3_shape], [s1_var, s2_var, s3_var],
                           mask_shape, mask_var, lstm_size, win, output_classes, fusiontype, w_init_fn,
                           use_peepholes)
+
+
+def create_pretrained_model(s1_ae, s1_lstm, s2_ae, s2_lstm, s3_ae, s3_lstm, s1_shape, s1_var, s2_shape, s2_var,
+                            s3_shape, s3_var, mask_shape, mask_var, lstm_size=250, win=None, output_classes=26,
+                            fusiontype='concat', w_init_fn=init.Orthogonal(), use_peepholes=True,
+                            use_blstm_substream=False):
+    """`modelzoo/adenet_3stream.py:12-142`: sub-stream LSTMs loaded from LSTM `.mat` dicts (`custom/layers.py:28-52`)."""
+    return _nstream.build([s1_ae, s2_ae, s3_ae], [s1_shape, s2_shape, s3_shape], [s1_var, s2_var, s3_var],
+                          mask_shape, mask_var, lstm_size, win, output_classes, fusiontype, w_init_fn,
+                          use_peepholes, lstm_weights=[s1_lstm, s2_lstm, s3_lstm],
+                          use_blstm_substream=use_blstm_substream)

@@ -20,6 +20,13 @@ def create_pretrained_encoder(weights, biases, incoming):
 
 def create_model(dbn, input_shape, input_var, mask_shape, mask_var, dct_shape, dct_var, lstm_size=250,
                  win=None, output_classes=26):
+    return _build(dbn, input_shape, input_var, mask_shape, mask_var, dct_shape, dct_var, lstm_size, win, output_classes,
+                  False)
+
+
+def _build(dbn, input_shape, input_var, mask_shape, mask_var, dct_shape, dct_var, lstm_size, win, output_classes, dropout):
+    """dropout=True is `modelzoo/adenet_v1_1.py:47-104`: dropout before each BLSTM, the first BLSTM 2*lstm_size wide."""
+    from ..layers import DropoutLayer
     weights, biases = extract_dbn_weights(dbn)
     gate_parameters, cell_parameters = gates(init.Orthogonal())
     l_in = InputLayer(input_shape, input_var, 'input')
@@ -32,9 +39,12 @@ def create_model(dbn, input_shape, input_var, mask_shape, mask_var, dct_shape, d
     l_reshape2 = ReshapeLayer(l_encoder_bn, (None, None, encoder_len), name='reshape2')
     l_delta = DeltaLayer(l_reshape2, win, name='delta')
     l_concat = ConcatLayer([l_delta, l_dct], axis=2, name='concat')
-    l_lstm, l_lstm_back = create_blstm(l_concat, l_mask, lstm_size, cell_parameters, gate_parameters, 'lstm1')
+    l_top = DropoutLayer(l_concat, name='dropout1') if dropout else l_concat
+    l_lstm, l_lstm_back = create_blstm(l_top, l_mask, lstm_size * 2 if dropout else lstm_size, cell_parameters,
+                                       gate_parameters, 'lstm1')
     l_sum1 = ElemwiseSumLayer([l_lstm, l_lstm_back], name='sum1')
-    l_lstm2, l_lstm2_back = create_blstm(l_sum1, l_mask, lstm_size * 2, cell_parameters, gate_parameters,
+    l_top = DropoutLayer(l_sum1, name='dropout2') if dropout else l_sum1
+    l_lstm2, l_lstm2_back = create_blstm(l_top, l_mask, lstm_size * 2, cell_parameters, gate_parameters,
                                          'lstm2')
     l_sum2 = ElemwiseSumLayer([l_lstm2, l_lstm2_back])
     l_forward_slice1 = SliceLayer(l_sum2, -1, 1, name='slice1')

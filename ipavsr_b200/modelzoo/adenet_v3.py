@@ -24,12 +24,19 @@ extract_weights = extract_dbn_weights
 
 def create_model(ae, diff_ae, input_shape, input_var, mask_shape, mask_var, dct_shape, dct_var,
                  diff_shape, diff_var, lstm_size=250, win=None, output_classes=26, fusiontype='sum'):
+    return _build(ae, diff_ae, input_shape, input_var, mask_shape, mask_var, dct_shape, dct_var, diff_shape, diff_var,
+                  lstm_size, win, output_classes, fusiontype)
+
+
+def _build(ae, diff_ae, input_shape, input_var, mask_shape, mask_var, dct_shape, dct_var, diff_shape, diff_var,
+           lstm_size, win, output_classes, fusiontype):
+    """dct_shape=None drops the DCT stream (`modelzoo/adenet_v6.py:64-175`)."""
     bn_weights, bn_biases = extract_weights(ae)
     diff_weights, diff_biases = extract_weights(diff_ae)
     gate_parameters, cell_parameters = gates(init.Orthogonal())
     l_raw = InputLayer(input_shape, input_var, 'raw_im')
     l_mask = InputLayer(mask_shape, mask_var, 'mask')
-    l_dct = InputLayer(dct_shape, dct_var, 'dct')
+    l_dct = InputLayer(dct_shape, dct_var, 'dct') if dct_shape is not None else None
     l_diff = InputLayer(diff_shape, diff_var, 'diff_im')
 
     l_reshape1_raw = ReshapeLayer(l_raw, (-1, input_shape[-1]), name='reshape1_raw')
@@ -54,12 +61,14 @@ def create_model(ae, diff_ae, input_shape, input_var, mask_shape, mask_var, dct_
 
     l_delta_raw_drop = DropoutLayer(l_delta_raw, name='dropout_raw')
     l_lstm_raw = stream_lstm(l_delta_raw_drop, 'lstm_raw')
-    l_dct_drop = DropoutLayer(l_dct, p=0.2, name='dropout_dct')
-    l_lstm_dct = stream_lstm(l_dct_drop, 'lstm_dct')
+    streams = [l_lstm_raw]
+    if l_dct is not None:
+        l_dct_drop = DropoutLayer(l_dct, p=0.2, name='dropout_dct')
+        streams.append(stream_lstm(l_dct_drop, 'lstm_dct'))
     l_delta_diff_drop = DropoutLayer(l_delta_diff, name='dropout_diff')
-    l_lstm_diff = stream_lstm(l_delta_diff_drop, 'lstm_diff')
+    streams.append(stream_lstm(l_delta_diff_drop, 'lstm_diff'))
 
-    l_fuse = fuse(fusiontype, [l_lstm_raw, l_lstm_dct, l_lstm_diff],
+    l_fuse = fuse(fusiontype, streams,
                   {'sum': 'sum1', 'adasum': 'adasum1', 'concat': 'concat'}, strict=False)
     l_drop_agg = DropoutLayer(l_fuse, name='dropout_agg')
     f_lstm_agg, b_lstm_agg = create_blstm(l_drop_agg, l_mask, lstm_size * 2, cell_parameters, gate_parameters,

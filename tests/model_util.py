@@ -104,8 +104,100 @@ def build(name, rng, C=7, H=12, win=3, fusiontype='sum'):
                                                          (None, None, dims[2]), v('s3'), (None, None, dims[3]), v('s4'),
                                                          (None, None), m, H, win, C, fusiontype)
         return dict(net=net, names=['s1_im', 's2_im', 's3_im', 's4_im'], dims=dims, level='frame', fuse=fuse)
+    if name in VARIANTS:
+        return _build_variant(name, rng, C, H, win, fusiontype, v, m)
     raise KeyError(name)
 
+
+def lstm_mat(rng, I, H, prefixes=('f_lstm', 'b_lstm')):
+    """An LSTM `.mat` dict in the layout of `modelzoo/deltanet_majority_vote.py:183-194`."""
+    d = {}
+    for pre in prefixes:
+        for g in ('ingate', 'forgetgate', 'cell', 'outgate'):
+            d['%s_w_in_to_%s' % (pre, g)] = rng.normal(0, 0.2, (I, H)).astype('float32')
+            d['%s_w_hid_to_%s' % (pre, g)] = rng.normal(0, 0.2, (H, H)).astype('float32')
+            d['%s_b_%s' % (pre, g)] = rng.normal(0, 0.1, (1, H)).astype('float32')
+    return d
+
+
+def _build_variant(name, rng, C, H, win, fusiontype, v, m):
+    """the remaining builder variants (same layers, different wiring)."""
+    Z = modelzoo
+    D, Dd = 40, 18
+    sh = lambda d: (None, None, d)
+    ms = (None, None)
+    dbn = lambda: FakeDBN(*enc_weights(rng, D))
+    rect = ('rectify', 'rectify', 'rectify', 'linear')
+    if name == 'adenet_v1_1':
+        net = Z.adenet_v1_1.create_model(dbn(), sh(D), v('x'), ms, m, sh(Dd), v('dct'), H, win, C)
+        return dict(net=net, names=['input', 'dct'], dims=[D, Dd], level='seq')
+    if name == 'adenet_v2_1':
+        net, fuse = Z.adenet_v2_1.create_model(dbn(), dbn(), sh(D), v('x'), ms, m, sh(D), v('diff'), H, win, C, fusiontype)
+        return dict(net=net, names=['raw_im', 'diff_im'], dims=[D, D], level='seq', fuse=fuse)
+    if name in ('adenet_v2_2', 'adenet_v2_nodelta', 'adenet_v2_4', 'adenet_2stream', 'adenet_2stream_pretrained',
+                'adenet_2stream_pretrained_blstm'):
+        dims = [D, 24]
+        aes = [ae_tuple(rng, d, acts=rect) for d in dims]
+        if name == 'adenet_v2_2':
+            net, fuse = Z.adenet_v2_2.create_model(aes[0], aes[1], sh(dims[0]), v('s1'), ms, m, sh(dims[1]), v('s2'), H,
+                                                   win, C, fusiontype)
+        elif name == 'adenet_v2_nodelta':
+            net, fuse = Z.adenet_v2_nodelta.create_model(aes[0], aes[1], sh(dims[0]), v('s1'), ms, m, sh(dims[1]), v('s2'),
+                                                         H, C, fusiontype)
+        elif name == 'adenet_v2_4':
+            net, fuse = Z.adenet_v2_4.create_model(aes[0], aes[1], sh(dims[0]), v('s1'), ms, m, sh(dims[1]), v('s2'), H,
+                                                   win, C, fusiontype)
+            return dict(net=net, names=['raw_im', 'diff_im'], dims=dims, level='frame', fuse=fuse)
+        elif name == 'adenet_2stream':
+            net, fuse = Z.adenet_2stream.create_model(aes[0], aes[1], sh(dims[0]), v('s1'), sh(dims[1]), v('s2'), ms, m, H,
+                                                      win, C, fusiontype)
+        else:
+            mats = [lstm_mat(rng, 30, H), lstm_mat(rng, 30, H)]
+            net, fuse = Z.adenet_2stream.create_pretrained_model(
+                aes[0], mats[0], aes[1], mats[1], sh(dims[0]), v('s1'), sh(dims[1]), v('s2'), ms, m, H, win, C, fusiontype,
+                init.Orthogonal(), True, name.endswith('blstm'))
+            return dict(net=net, names=['s1_im', 's2_im'], dims=dims, level='frame', fuse=fuse, mats=mats)
+        return dict(net=net, names=['s1_im', 's2_im'], dims=dims, level='frame', fuse=fuse)
+    if name == 'adenet_v2_3':
+        net, fuse = Z.adenet_v2_3.create_model(dbn(), sh(D), v('x'), ms, m, sh(Dd), v('dct'), H, win, C, fusiontype)
+        return dict(net=net, names=['input', 'dct'], dims=[D, Dd], level='frame', fuse=fuse)
+    if name == 'adenet_v4':
+        net, fuse = Z.adenet_v4.create_model(dbn(), sh(D), v('x'), ms, m, sh(Dd), v('dct'), H, win, C)
+        return dict(net=net, names=['input', 'dct'], dims=[D, Dd], level='seq', fuse=fuse)
+    if name == 'adenet_v5':
+        net, fuse = Z.adenet_v5.create_model(dbn(), dbn(), sh(D), v('x'), ms, m, sh(Dd), v('dct'), sh(D), v('diff'), H, win,
+                                             C, fusiontype == 'adasum')
+        return dict(net=net, names=['raw_im', 'dct', 'diff_im'], dims=[D, Dd, D], level='seq', fuse=fuse)
+    if name == 'adenet_v6':
+        net, fuse = Z.adenet_v6.create_model(dbn(), dbn(), sh(D), v('x'), ms, m, sh(D), v('diff'), H, win, C,
+                                             fusiontype == 'adasum')
+        return dict(net=net, names=['raw_im', 'diff_im'], dims=[D, D], level='seq', fuse=fuse)
+    if name in ('adenet_3stream_dct', 'adenet_3stream_dropout', 'adenet_3stream_pretrained'):
+        dims = [D, 24, 32]
+        aes = [ae_tuple(rng, d, acts=rect) for d in dims]
+        shapes_vars = [sh(dims[0]), v('s1'), sh(dims[1]), v('s2'), sh(dims[2]), v('s3')]
+        if name == 'adenet_3stream_dct':
+            net, fuse = Z.adenet_3stream_dct.create_model(aes[0], aes[1], *(shapes_vars + [ms, m, H, win, C, fusiontype]))
+        elif name == 'adenet_3stream_dropout':
+            net, fuse = Z.adenet_3stream_dropout.create_model(aes[0], aes[1], aes[2],
+                                                              *(shapes_vars + [ms, m, H, win, C, fusiontype]))
+        else:
+            mats = [lstm_mat(rng, 30, H, ('f_lstm',)) for _ in dims]
+            net, fuse = Z.adenet_3stream.create_pretrained_model(aes[0], mats[0], aes[1], mats[1], aes[2], mats[2],
+                                                                 *(shapes_vars + [ms, m, H, win, C, fusiontype]))
+            return dict(net=net, names=['s1_im', 's2_im', 's3_im'], dims=dims, level='frame', fuse=fuse, mats=mats)
+        return dict(net=net, names=['s1_im', 's2_im', 's3_im'], dims=dims, level='frame', fuse=fuse)
+    if name in ('lstm_classifier_majority_vote', 'lstm_classifier_majority_vote_lstm'):
+        net = Z.lstm_classifier_majority_vote.create_model(sh(Dd), v('x'), ms, m, H, C, init.GlorotUniform(), True,
+                                                           not name.endswith('_lstm'))
+        return dict(net=net, names=['input'], dims=[Dd], level='frame')
+    raise KeyError(name)
+
+
+VARIANTS = ['adenet_v1_1', 'adenet_v2_1', 'adenet_v2_2', 'adenet_v2_3', 'adenet_v2_4', 'adenet_v2_nodelta', 'adenet_v4',
+            'adenet_v5', 'adenet_v6', 'adenet_2stream', 'adenet_2stream_pretrained', 'adenet_2stream_pretrained_blstm',
+            'adenet_3stream_dct', 'adenet_3stream_dropout', 'adenet_3stream_pretrained', 'lstm_classifier_majority_vote',
+            'lstm_classifier_majority_vote_lstm']
 
 ALL = ['deltanet', 'deltanet_majority_vote', 'deltanet_v1', 'lstm_classifier_baseline', 'adenet_v1', 'adenet_v2',
        'adenet_v3', 'adenet_3stream', 'adenet_4stream']

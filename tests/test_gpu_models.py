@@ -35,10 +35,25 @@ def _oracle(net, feed, win, y, mask, level, dm, dt=np.float64):
     return o.loss_and_grads(feed, win, y, mask, loss, deterministic=False, dropout_masks=dm, update_bn=False)
 
 
+def _fusions(name):
+    return ['sum', 'adasum', 'concat'] if name in ('adenet_v2', 'adenet_v3', 'adenet_3stream', 'adenet_4stream') else ['sum']
+
+
 @pytest.mark.parametrize('name', MU.ALL)
 def test_forward_backward_parity(name):
-    for fusiontype in (['sum', 'adasum', 'concat'] if name in ('adenet_v2', 'adenet_v3', 'adenet_3stream',
-                                                                'adenet_4stream') else ['sum']):
+    _check_forward_backward(name, _fusions(name))
+
+
+@pytest.mark.parametrize('name', MU.VARIANTS)
+def test_builder_variants_forward_backward_parity(name):
+    """the remaining modelzoo variants through the same engine, against the oracle."""
+    fus = {'adenet_v5': ['sum', 'adasum'], 'adenet_v2_3': ['adasum'], 'adenet_v4': ['sum'], 'adenet_v1_1': ['sum'],
+           'adenet_v2_2': ['concat', 'adasum']}.get(name, ['concat'])
+    _check_forward_backward(name, fus)
+
+
+def _check_forward_backward(name, fusiontypes):
+    for fusiontype in fusiontypes:
         spec, net, feed, mask, y, dm, win = _case(name, hash(name) % 1000, fusiontype)
         loss_ref, out_ref, grads_ref = _oracle(net, feed, win, y, mask, spec['level'], dm)
         eng = Engine(net, gemm_mode='fp32')

@@ -251,3 +251,59 @@ def test_squared_error_l2_objective_expression_and_oracle_gradients():
         wm = keep.copy(); wm[idx] -= eps; p.set_value(wm); dn = value()
         p.set_value(keep)
         assert abs((up - dn) / (2 * eps) - g[idx]) <= 2e-3 * max(abs(g[idx]), 1e-3), p.name
+
+
+@pytest.mark.parametrize('name', MU.VARIANTS)
+def test_every_builder_variant_builds_and_runs_through_the_oracle(name):
+    """the remaining modelzoo variants are wiring over the same layers; each builds with the reference's
+    positional signature, round-trips its parameter list, and its oracle forward gives normalised class probabilities."""
+    from oracle.net import OracleNet
+    rng = np.random.default_rng(4)
+    spec = MU.build(name, rng, fusiontype='sum' if name in ('adenet_v4', 'adenet_v5', 'adenet_v2_3') else 'concat')
+    net = spec['net']
+    assert net.output_shape[-1] == 7 and (len(net.output_shape) == 3) == (spec['level'] == 'frame')
+    vals = L.get_all_param_values(net)
+    L.set_all_param_values(net, vals)
+    N, T_ = 3, 6
+    xs, mask, lens = MU.make_feed(rng, N, T_, spec['dims'])
+    feed = dict(zip(spec['names'], xs))
+    feed['mask'] = mask
+    out = OracleNet(net, np.float64).forward(feed, 3, deterministic=True)
+    assert out.shape == ((N, T_, 7) if spec['level'] == 'frame' else (N, 7))
+    np.testing.assert_allclose(out.sum(-1), 1.0, rtol=1e-9)
+
+
+def test_builder_variant_wiring_details():
+    rng = np.random.default_rng(5)
+    by = lambda spec: {l.name: l for l in L.get_all_layers(spec['net'])}
+    # files with a local create_blstm / create_lstm (default use_peepholes=True): the aggregate has peepholes
+    for name in ('adenet_v2_2', 'adenet_v2_nodelta', 'adenet_v2_1'):
+        assert by(MU.build(name, rng, fusiontype='concat'))['f_lstm_agg'].peepholes, name
+    for name in ('adenet_2stream', 'adenet_3stream_dct', 'adenet_3stream_dropout'):     # custom.layers.create_blstm: none
+        assert not by(MU.build(name, rng, fusiontype='concat'))['f_lstm_agg'].peepholes, name
+    b = by(MU.build('adenet_v2_nodelta', rng, fusiontype='concat'))
+    assert not [n for n in b if n and n.startswith('delta')] and b['lstm_s1'].num_inputs == 10
+    b = by(MU.build('adenet_v2_4', rng, fusiontype='concat'))
+    assert 'b_lstm_agg' not in b and b['f_lstm_agg'].peepholes and b['f_lstm_agg'].num_inputs == 24
+    names = [l.name for l in L.get_all_layers(MU.build('adenet_v2_4', rng, fusiontype='sum')['net'])]
+    assert names[-4:] == ['f_lstm_agg', None, 'softmax', 'output']
+    b = by(MU.build('adenet_3stream_dropout', rng, fusiontype='concat'))
+    assert b['lstm_s2'].num_units == 24 and b['f_lstm_agg'].num_units == 24 and b['f_lstm_agg'].num_inputs == 72
+    assert b['concat_dropout'].p == 0.5 and b['reshape3'].shape == (-1, 24)
+    b = by(MU.build('adenet_3stream_dct', rng, fusiontype='concat'))
+    assert 'fc1_s3' not in b and b['delta_s3'].output_shape[-1] == 96 and b['lstm_s3'].num_inputs == 96
+    b = by(MU.build('adenet_v4', rng))
+    assert b['lstm_bn'].num_units == 24 and b['lstm_bn'].peepholes and b['dropout_dct'].p == 0.2 and 'b_lstm_agg' not in b
+    b = by(MU.build('adenet_v6', rng))
+    assert 'dct' not in b and 'sum1' in b and b['f_lstm_agg'].num_units == 24
+    assert 'adasum1' in by(MU.build('adenet_v5', rng, fusiontype='adasum'))
+    b = by(MU.build('adenet_v1_1', rng))
+    assert b['f_lstm1'].num_units == 24 and b['dropout1'].input_layer is b['concat'] and b['dropout2'].input_layer is b['sum1']
+    # pretrained sub-stream LSTMs: the .mat weights land in the layers; forward + backward are summed per stream
+    spec = MU.build('adenet_2stream_pretrained_blstm', rng, fusiontype='concat')
+    b = by(spec)
+    np.testing.assert_array_equal(b['b_lstm_s2'].W_hid_to_cell.get_value(), spec['mats'][1]['b_lstm_w_hid_to_cell'])
+    np.testing.assert_array_equal(b['f_lstm_s1'].W_in_to_ingate.get_value(), spec['mats'][0]['f_lstm_w_in_to_ingate'])
+    assert b['b_lstm_s1'].backwards and b['sum_b_lstm_s1'].input_layers == [b['f_lstm_s1'], b['b_lstm_s1']]
+    b = by(MU.build('lstm_classifier_majority_vote_lstm', rng))
+    assert 'b_lstm' not in b and b['lstm'].peepholes
