@@ -187,6 +187,14 @@ def _build_variant(name, rng, C, H, win, fusiontype, v, m):
                                                                  *(shapes_vars + [ms, m, H, win, C, fusiontype]))
             return dict(net=net, names=['s1_im', 's2_im', 's3_im'], dims=dims, level='frame', fuse=fuse, mats=mats)
         return dict(net=net, names=['s1_im', 's2_im', 's3_im'], dims=dims, level='frame', fuse=fuse)
+    if name == 'avnet':
+        dims = [D, 24]
+        subs = []
+        for k, d in enumerate(dims):
+            W, b = enc_weights(rng, d)
+            subs.append(Z.avnet.create_pretrained_substream(W, b, sh(d), v('s%d' % k), ms, m, ('visual', 'audio')[k], H, win))
+        net, fuse = Z.avnet.create_model(subs, ms, m, H, C, fusiontype)
+        return dict(net=net, names=['input_visual', 'input_audio'], dims=dims, level='frame', fuse=fuse)
     if name in ('lstm_classifier_majority_vote', 'lstm_classifier_majority_vote_lstm'):
         net = Z.lstm_classifier_majority_vote.create_model(sh(Dd), v('x'), ms, m, H, C, init.GlorotUniform(), True,
                                                            not name.endswith('_lstm'))
@@ -196,7 +204,7 @@ def _build_variant(name, rng, C, H, win, fusiontype, v, m):
 
 VARIANTS = ['adenet_v1_1', 'adenet_v2_1', 'adenet_v2_2', 'adenet_v2_3', 'adenet_v2_4', 'adenet_v2_nodelta', 'adenet_v4',
             'adenet_v5', 'adenet_v6', 'adenet_2stream', 'adenet_2stream_pretrained', 'adenet_2stream_pretrained_blstm',
-            'adenet_3stream_dct', 'adenet_3stream_dropout', 'adenet_3stream_pretrained', 'lstm_classifier_majority_vote',
+            'adenet_3stream_dct', 'adenet_3stream_dropout', 'adenet_3stream_pretrained', 'avnet', 'lstm_classifier_majority_vote',
             'lstm_classifier_majority_vote_lstm']
 
 ALL = ['deltanet', 'deltanet_majority_vote', 'deltanet_v1', 'lstm_classifier_baseline', 'adenet_v1', 'adenet_v2',

@@ -14,7 +14,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--batch', default='128,4096,32768')
 ap.add_argument('--steps', type=int, default=20)
 ap.add_argument('--json', default=None)
+ap.add_argument('--profile', action='store_true', help='per-entry-point device time of one step (CUDA events per call)')
+ap.add_argument('--mode', default='f16x3', help='GEMM arithmetic: f16x3 (tcgen05, fp32 parity) | tf32x3 | fp32 (FFMA)')
 args = ap.parse_args()
+os.environ['IPAVSR_GEMM_MODE'] = args.mode
 
 from ipavsr_b200 import layers as L
 from ipavsr_b200.nonlinearities import sigmoid, linear
@@ -49,10 +52,23 @@ for B in [int(b) for b in args.batch.split(',')]:
     dt = (time.perf_counter() - t0) / args.steps
     nparam = sum(sizes[i] * sizes[i + 1] for i in range(8))
     flop = B * (6.0 * nparam - 2.0 * sizes[0] * sizes[1])
-    r = {'batch': B, 'ms_per_step': dt * 1e3, 'frames_per_s': B / dt, 'model_tflops': flop / dt / 1e12,
+    r = {'mode': args.mode, 'batch': B, 'ms_per_step': dt * 1e3, 'frames_per_s': B / dt, 'model_tflops': flop / dt / 1e12,
          'loss': float(loss), 'launches_per_step': (lib.ipavsr_launch_count() - n0) / args.steps}
     results.append(r)
     print(json.dumps(r), flush=True)
+    if args.profile:
+        from ipavsr_b200 import engine as E, _lib
+        prof = E._Profiler(by_shape=True)
+        orig = _lib.call
+        _lib.call = E._lib.call = prof.call
+        for _ in range(3):
+            net.train_iter_(X, y)
+        summ = prof.summary()
+        _lib.call = E._lib.call = orig
+        tot = sum(t for n, t in summ.values()) / 3
+        print('  batch %d: sum of kernels %.3f ms/step (wall %.3f)' % (B, tot, dt * 1e3))
+        for name, (n, t) in sorted(summ.items(), key=lambda kv: -kv[1][1])[:14]:
+            print('    %-64s n/step=%4.1f %8.3f ms/step' % (name, n / 3, t / 3), flush=True)
     del net
 if args.json:
     json.dump(results, open(args.json, 'w'), indent=1)
