@@ -103,17 +103,25 @@ class NeuralNet(object):
         return X.reshape(X.shape[0], 1, -1)
 
     def fit(self, X, y, epochs=None):
+        """nolearn's train loop.  The training matrix is uploaded ONCE and stays in HBM (the AVLetters / OuluVS frame matrices
+        are 0.1-1 GB); every batch is a row-slice view of it, so a step moves no input bytes over the host link — only the
+        loss comes back, like the reference's `train_iter_` return value."""
+        import torch
         self.initialize()
-        X, y = np.asarray(X, dtype=np.float32), np.asarray(y, dtype=np.float32)
-        tr, va = train_split(len(X), self.eval_size)
-        Xt, yt, Xv, yv = X[tr], y[tr], X[va], y[va]
+        same = y is X
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        dev = self.train_iter_.engine.device
+        Xd = torch.from_numpy(X).to(dev)
+        yd = Xd if same else torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(dev)
+        tr, va = train_split(len(X), self.eval_size)           # validation = the first len(va) rows, training = the rest
+        Xt, yt, Xv, yv = Xd[len(va):], yd[len(va):], Xd[:len(va)], yd[:len(va)]
         for _ in range(epochs or self.max_epochs):
             tl, tn, vl, vn = [], [], [], []
             for s in self._batches(len(Xt)):
-                tl.append(float(self.train_iter_(self._rows(Xt[s]), yt[s])))
+                tl.append(float(self.train_iter_(Xt[s].unsqueeze(1), yt[s])))
                 tn.append(s.stop - s.start)
             for s in self._batches(len(Xv)):
-                vl.append(float(self.eval_iter_(self._rows(Xv[s]), yv[s])))
+                vl.append(float(self.eval_iter_(Xv[s].unsqueeze(1), yv[s])))
                 vn.append(s.stop - s.start)
             info = {'epoch': len(self.train_history_) + 1, 'train_loss': float(np.average(tl, weights=tn)),
                     'valid_loss': float(np.average(vl, weights=vn)) if vl else float('nan')}

@@ -41,19 +41,26 @@ for B in [int(b) for b in args.batch.split(',')]:
     X = torch.randn(B, 1, sizes[0]).pin_memory().numpy()
     y = X.reshape(B, sizes[0])
     lib = net.train_iter_.engine.lib
-    for _ in range(3):
-        loss = net.train_iter_(X, y)
-    torch.cuda.synchronize()
-    n0 = lib.ipavsr_launch_count()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        loss = net.train_iter_(X, y)               # returns the loss to the host: synchronises every step, like fit()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / args.steps
     nparam = sum(sizes[i] * sizes[i + 1] for i in range(8))
     flop = B * (6.0 * nparam - 2.0 * sizes[0] * sizes[1])
-    r = {'mode': args.mode, 'batch': B, 'ms_per_step': dt * 1e3, 'frames_per_s': B / dt, 'model_tflops': flop / dt / 1e12,
-         'loss': float(loss), 'launches_per_step': (lib.ipavsr_launch_count() - n0) / args.steps}
+    Xd = torch.from_numpy(X).cuda()
+    yd = Xd.reshape(B, sizes[0])
+    r = {'mode': args.mode, 'batch': B}
+    # 'resident': what NeuralNet.fit does (the training matrix lives in HBM, batches are row views; the loss is read back
+    # every step); 'host_batches': every step uploads its batch and targets from pinned host memory
+    for tag, (a, b) in (('resident', (Xd, yd)), ('host_batches', (X, y))):
+        for _ in range(3):
+            loss = net.train_iter_(a, b)
+        torch.cuda.synchronize()
+        n0 = lib.ipavsr_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            loss = net.train_iter_(a, b)           # returns the loss to the host: synchronises every step, like fit()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        r[tag] = {'ms_per_step': dt * 1e3, 'frames_per_s': B / dt, 'model_tflops': flop / dt / 1e12}
+        r['launches_per_step'] = (lib.ipavsr_launch_count() - n0) / args.steps
+    r['loss'] = float(loss)
     results.append(r)
     print(json.dumps(r), flush=True)
     if args.profile:
