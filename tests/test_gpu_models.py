@@ -50,14 +50,6 @@ def test_forward_backward_parity(name):
     _check_forward_backward(name, _fusions(name))
 
 
-@pytest.mark.parametrize('name', MU.VARIANTS)
-def test_builder_variants_forward_backward_parity(name):
-    """the remaining modelzoo variants through the same engine, against the oracle."""
-    fus = {'adenet_v5': ['sum', 'adasum'], 'adenet_v2_3': ['adasum'], 'adenet_v4': ['sum'], 'adenet_v1_1': ['sum'],
-           'adenet_v2_2': ['concat', 'adasum']}.get(name, ['concat'])
-    _check_forward_backward(name, fus)
-
-
 def _check_forward_backward(name, fusiontypes):
     for fusiontype in fusiontypes:
         spec, net, feed, mask, y, dm, win = _case(name, _seed(name), fusiontype)
