@@ -37,6 +37,23 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1 and b'ipavsr_gemm' in lib.ipavsr_last_error()
     rc = lib.ipavsr_delta_fwd(None, 4, None, 12, 1, 1, 4, 1, 1, None)
     assert rc == -1
+    # the entry points of SURVEY 8f ranks 3 and 4: bad arguments are refused before anything touches the device
+    one = ctypes.c_void_p(16)                       # a non-NULL, never dereferenced pointer
+    assert lib.ipavsr_dct_basis(None, 4, None, 8, 4, None) == -1
+    assert lib.ipavsr_dct_basis(one, 2, None, 8, 4, None) == -1 and b'ldb' in lib.ipavsr_last_error()
+    assert lib.ipavsr_dct_project(one, 8, one, 4, one, 2, 10, 8, 4, None) == -1          # ldo < K
+    assert lib.ipavsr_dct_project(one, 8, one, 4, one, 4, 65536 * 128, 8, 4, None) == -1  # more than 65535 frame tiles
+    assert lib.ipavsr_reorder(one, 12, one, 12, 5, 3, 4, 1, None) == -1                  # in place is not supported
+    assert lib.ipavsr_reorder(one, 8, ctypes.c_void_p(32), 12, 5, 3, 4, 1, None) == -1   # ldx < d1*d2
+    assert lib.ipavsr_align_fill(one, 8, ctypes.c_void_p(32), 8, None, one, None, 3, 8, 10, None) == -1
+    assert lib.ipavsr_gather_cols(one, 8, one, one, 2, 10, 4, None) == -1                # ldo < K
+    assert lib.ipavsr_col_abs_sum(one, 2, one, 10, 4, None) == -1                        # ldx < F
+    assert lib.ipavsr_squared_error(one, 4, one, 8, one, None, 0, 10, 8, 1.0, None) == -1   # ldp < F
+    assert lib.ipavsr_l2_penalty(one, None, 100, None, one, one, 1.0, None) == -1
+    assert lib.ipavsr_zigzag_indices(0, 4, None) == -1
+    # empty problems are a no-op that needs no device either
+    assert lib.ipavsr_dct_project(one, 8, one, 4, one, 4, 0, 8, 4, None) == 0
+    assert lib.ipavsr_align_fill(one, 8, ctypes.c_void_p(32), 8, one, one, None, 3, 8, 0, None) == 0
 
 
 def test_adenet_v2_layer_and_param_order():
