@@ -55,6 +55,9 @@ extern "C" {
 
 const char* ipavsr_last_error(void);
 int ipavsr_version(void);
+/* hash of the sources (csrc/*.cu, *.cuh, this header) the library was built from: the Python loader compares it with the
+ * tree it runs from and rebuilds (or refuses to run) a stale library instead of calling it with a changed ABI */
+const char* ipavsr_source_hash(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches counter) */
 uint64_t ipavsr_launch_count(void);
 /* device properties the host side sizes grids with; returns 0 or a negative code */
@@ -192,6 +195,20 @@ int ipavsr_slice_last(const float* src, int lds, float* dst, int ldd, int N, int
 int ipavsr_batch_gather(const float* data, int ldd, const int64_t* integral_lens, const int32_t* seqlens,
                         const int32_t* idxs, const uint8_t* y, float* X, int ldx, uint8_t* mask, uint8_t* y_batch,
                         int N, int T, int F, void* stream);
+/* ---- packed / length-sorted execution of a padded batch (the padding algebra of SURVEY A.2; utils/datagen.py:129-139
+ * zero-pads every utterance to T, modelzoo/pretrained_encoder.py:4-9 then encodes all N*T rows) ---------------------------
+ * dst[r, :] = idx[r] >= 0 ? src[idx[r], :] : fill_row[:]  (fill_row NULL: zeros) for rows of row_bytes BYTES with the
+ * given byte pitches; 16-byte accesses when every pointer / pitch / row_bytes allows.  `src` may be PINNED HOST memory
+ * (device-accessible under UVA): only the gathered rows then cross PCIe (ragged upload of the valid frames).
+ * The engine uses it to pack the valid frames of a padded (N*T, F) stream in length-sorted utterance order (+ one zero
+ * row whose encoder output is the constant every padding frame takes), to expand the bottleneck back to (N*T, F), and
+ * to permute / un-permute utterances of the other streams, masks, targets and outputs. */
+int ipavsr_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int row_bytes,
+                       const int32_t* idx, const void* fill_row, int64_t rows, void* stream);
+/* out[c] (+)= sum of X[r, c] over the rows with (rowmask[r] != 0) != invert: the gradient of the shared constant row
+ * (all padding rows of the expanded bottleneck) in the backward of that expansion. */
+int ipavsr_colsum_masked(const float* X, int ldx, const uint8_t* rowmask, int invert, float* out, int M, int N,
+                         int accumulate, void* stream);
 /* ---- f2: evaluation on the device  (runners/2stream_dct.py:48-81 evaluate_model2; every runner's evaluate_model)
  * probs (N*T, C; ldp): for utterance i, the argmax over the classes of each of its first seq_len = sum(mask[i,:]) frames
  * (mask NULL: all T frames), a vote per class, pred[i] = the class with most votes; ties go to the lowest class index

@@ -22,6 +22,7 @@ I64 = C.c_int64
 _SIGS = {
     'ipavsr_last_error': (C.c_char_p, []),
     'ipavsr_version': (I, []),
+    'ipavsr_source_hash': (C.c_char_p, []),
     'ipavsr_launch_count': (U64, []),
     'ipavsr_device_info': (I, [P, P, P, P]),
     'ipavsr_gemm': (I, [I, I, I, I, I, I, P, I, P, I, P, I, P, I, I, P, U64, P]),
@@ -76,6 +77,8 @@ _SIGS = {
     'ipavsr_col_abs_sum': (I, [P, I, P, I64, I, P]),
     'ipavsr_reorder': (I, [P, I, P, I, I64, I, I, I, P]),
     'ipavsr_align_fill': (I, [P, I, P, I, P, P, P, I, I, I64, P]),
+    'ipavsr_gather_rows': (I, [P, I64, P, I64, I, P, P, I64, P]),
+    'ipavsr_colsum_masked': (I, [P, I, P, I, P, I, I, I, P]),
     'ipavsr_debug_gemm_timestamps': (I, [P]),
     'ipavsr_debug_lstm_timestamps': (I, [P]),
     'ipavsr_fill': (I, [P, U64, F, P]),
@@ -95,14 +98,24 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build
+    from . import build
+    want = build.source_hash()
+    if not os.path.exists(LIB_PATH) or build.built_hash() != want:
+        # missing or stale (sources edited since the last build): rebuild in-tree when nvcc is there, otherwise refuse —
+        # calling a library built from other sources through these signatures would corrupt arguments silently
+        if not os.path.exists(build.NVCC):
+            raise RuntimeError('libipavsr_b200.so is %s and nvcc (%s) is not available to build it'
+                               % ('missing' if not os.path.exists(LIB_PATH) else 'stale', build.NVCC))
         build.build()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    got = lib.ipavsr_source_hash().decode()
+    if got != want:
+        raise RuntimeError('libipavsr_b200.so was built from other sources (hash %s, tree %s): run python -m ipavsr_b200.build'
+                           % (got, want))
     _lib = lib
     return lib
 

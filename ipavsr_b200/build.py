@@ -12,17 +12,29 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 
-def _stale(objs_src):
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = objs_src + glob.glob(os.path.join(SRC, '*.cuh')) + [os.path.join(HERE, '..', 'include', 'ipavsr_b200.h')]
-    return any(os.path.getmtime(d) > t for d in deps)
+def source_hash():
+    """Hash of everything the library is built from; the .so exports the value it was built with (ipavsr_source_hash)."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(SRC, '*.cu')) + glob.glob(os.path.join(SRC, '*.cuh'))) + [
+            os.path.join(HERE, '..', 'include', 'ipavsr_b200.h')]:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, 'rb').read())
+    return h.hexdigest()[:16]
+
+
+def built_hash():
+    """The source hash recorded next to the .so by the last build (None when there is none)."""
+    try:
+        return open(OUT + '.hash').read().strip() if os.path.exists(OUT) else None
+    except OSError:
+        return None
 
 
 def build(force=False, verbose=False):
     srcs = sorted(glob.glob(os.path.join(SRC, '*.cu')))
-    if not force and not _stale(srcs):
+    want = source_hash()
+    if not force and built_hash() == want:
         return OUT
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
@@ -31,11 +43,13 @@ def build(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + '.o')
         objs.append(o)
-        if not force and os.path.exists(o) and os.path.getmtime(o) > max(
+        is_rt = os.path.basename(s) == 'runtime.cu'          # carries the source hash: rebuilt with every build
+        if not force and not is_rt and os.path.exists(o) and os.path.getmtime(o) > max(
                 [os.path.getmtime(s)] + [os.path.getmtime(h) for h in glob.glob(os.path.join(SRC, '*.cuh'))] +
                 [os.path.getmtime(os.path.join(HERE, '..', 'include', 'ipavsr_b200.h'))]):
             continue
-        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', s, '-o', o]
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + (
+            ['-DIPAVSR_SRC_HASH="%s"' % want] if is_rt else []) + ['-c', s, '-o', o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -45,6 +59,8 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
     cmd = [NVCC, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.check_call(cmd)
+    with open(OUT + '.hash', 'w') as f:
+        f.write(want + '\n')
     return OUT
 
 

@@ -160,6 +160,25 @@ __device__ __forceinline__ float q_tanh(float x) {
   return fabsf(x) < 0.15f ? poly : big;
 }
 
+// bit t of the result: some utterance of the 32-utterance tile is unmasked at frame t (T <= 64); called by one full warp
+__device__ __forceinline__ unsigned long long q_tile_active(const uint8_t* __restrict__ mask, int tile, int N, int T,
+                                                            int lane) {
+  const int n = tile * QN + lane;
+  unsigned long long bits = 0ull;
+  if (n < N)
+    for (int t = 0; t < T; ++t)
+      if (mask[(size_t)n * T + t]) bits |= 1ull << t;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+  return bits;
+}
+// the next processed step after s whose frame is active, or T
+__device__ __forceinline__ int q_next_active(unsigned long long active, int s, int T, int backwards) {
+  for (int s2 = s + 1; s2 < T; ++s2)
+    if ((active >> (backwards ? (T - 1 - s2) : s2)) & 1ull) return s2;
+  return T;
+}
+
 struct CellF {
   float i, f, cin, o, c, h;
 };
@@ -213,6 +232,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_red[4];
   __shared__ int s_eh;
+  __shared__ unsigned long long s_active;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -236,10 +256,18 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
     mx = warp_max(mx);
     if (lane == 0) s_red[warp] = mx;
   }
+  // frames at which at least one utterance of the tile is unmasked; at the other frames every state is carried through
+  // (Lasagne's switch) and the step needs neither the recurrent product nor the exchange of h.  Every CTA of the
+  // cluster derives the same bit set from the same 32 mask rows.
+  if (warp == 4) {
+    const unsigned long long bits = q_tile_active(mask, tile, N, T, lane);
+    if (lane == 0) s_active = bits;
+  }
   q_fence_before();
   __syncthreads();
   q_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const unsigned long long active = s_active;
   if (tid == 0) {
     const float mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
     s_eh = 14 - ilogbf(mx);
@@ -278,10 +306,10 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       q_mbar_wait(&wbar, 0);
       uint32_t hphase[2] = {0, 0};
       long long c_wait = 0, c_issue = 0;
-      for (int s = 0; s < T; ++s) {
-        const int b = s & 1;
+      for (int s = q_next_active(active, -1, T, backwards), k = 0; s < T; s = q_next_active(active, s, T, backwards), ++k) {
+        const int b = k & 1;               // k counts the active steps: buffers and barrier phases alternate on it
         const long long c0 = q_clock();
-        if (s > 0) {
+        if (k > 0) {
           q_mbar_expect_tx(&hbar[b], (uint32_t)CS * 4096u);
           q_mbar_wait(&hbar[b], hphase[b]);
           hphase[b] ^= 1;
@@ -352,13 +380,31 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         xv[j] = (col_ok && n < N) ? __ldg(xw + ((size_t)n * T + t) * H4 + gcol) : 0.f;
       }
     };
-    fetch(backwards ? T - 1 : 0);
+    {
+      const int s0 = q_next_active(active, -1, T, backwards);
+      if (s0 < T) fetch(backwards ? (T - 1 - s0) : s0);
+    }
     long long e_wait = 0, e_ld = 0, e_math = 0, e_push = 0;
     const int nacc = (KSTEPS / 2) < QACC ? (KSTEPS / 2) : QACC;
+    int k = 0;                                         // active steps done so far
     for (int s = 0; s < T; ++s) {
       const int t = backwards ? (T - 1 - s) : s;
+      if (!((active >> t) & 1ull)) {
+        // every utterance of the tile is masked at this frame: the states pass through unchanged
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (u_ok && n_own[i] < N) {
+            const size_t row = (size_t)n_own[i] * T + t;
+            out[row * ldh + ug] = h_prev[i];
+            if (gates) *reinterpret_cast<float4*>(gates + row * H4 + 4 * ug) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cell) cell[row * H + ug] = c_prev[i];
+            if (hprev) hprev[row * ldh + ug] = h_prev[i];
+          }
+        continue;
+      }
+      const int s_next = q_next_active(active, s, T, backwards);
       const long long k0 = q_clock();
-      q_mbar_wait(&accbar, (uint32_t)(s & 1));
+      q_mbar_wait(&accbar, (uint32_t)(k & 1));
       q_fence_after();
       const long long k1 = q_clock();
       e_wait += k1 - k0;
@@ -397,7 +443,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       e_ld += k2 - k1;
 #pragma unroll
       for (int j = 0; j < QC; ++j) a[j] = a[j] * ms1 * ms2 + xv[j];
-      if (s + 1 < T) fetch(backwards ? (T - 2 - s) : (s + 1));
+      if (s_next < T) fetch(backwards ? (T - 1 - s_next) : s_next);
       // 4x4 transpose inside each group of 4 lanes (the 4 gates of a unit): afterwards a[4i + q] = gate q of utterance j0 + 4i + g
       const bool b0 = (g & 1) != 0, b1 = (g & 2) != 0;
 #pragma unroll
@@ -411,7 +457,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         if (b1) { x0 = r0; x1 = r1; } else { x2 = r0; x3 = r1; }
         a[4 * i] = x0; a[4 * i + 1] = x1; a[4 * i + 2] = x2; a[4 * i + 3] = x3;
       }
-      uint8_t* stg = sStage + (size_t)(s & 1) * 4096;
+      uint8_t* stg = sStage + (size_t)(k & 1) * 4096;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool mk = (mbits[i] >> t) & 1ull;
@@ -436,12 +482,12 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       }
       const long long k3 = q_clock();
       e_math += k3 - k2;
-      if (s + 1 < T) {
+      if (s_next < T) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // push my chunk of h_{t+1} into the next-step operand tile of every CTA of the cluster (my own included)
         if (tid < CS) {
-          const int nb = (s + 1) & 1;
+          const int nb = (k + 1) & 1;
           const uint32_t dst_hi = q_smem(sH + (size_t)nb * 2 * HBYTES + (size_t)rank * 2048);
           const uint32_t bar = q_mapa(q_smem(&hbar[nb]), (uint32_t)tid);
           q_bulk_s2s(q_mapa(dst_hi, (uint32_t)tid), q_smem(stg), 2048, bar);
@@ -449,6 +495,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         }
       }
       e_push += q_clock() - k3;
+      ++k;
     }
     if (dbg != nullptr && blockIdx.x == 0 && tid == 0) {
       dbg[2] = (unsigned long long)e_wait; dbg[3] = (unsigned long long)e_ld;
@@ -537,6 +584,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
   float* inbox = reinterpret_cast<float*>(sB + 16384); // [2 parities][CS sources][32 units][32 utterances]
   __shared__ __align__(8) uint64_t accbar, wbar, bready;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ unsigned long long s_active;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -551,10 +599,17 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // frames at which some utterance of the tile is unmasked (as in the forward kernel): at the others the gate gradients
+  // are zero and the state gradients pass through, so the step needs no recurrent product and no cluster exchange
+  if (warp == 4) {
+    const unsigned long long bits = q_tile_active(mask, tile, N, T, lane);
+    if (lane == 0) s_active = bits;
+  }
   q_fence_before();
   __syncthreads();
   q_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const unsigned long long active = s_active;
   if (tid == 0) {
     // W_hid[:, J_r]: all k rows x the CTA's 128 gate columns, K-major (j contiguous), from the fp16 split of the arena
     q_mbar_expect_tx(&wbar, (uint32_t)MB * 65536u);
@@ -570,9 +625,10 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
     // ===================== control warp =====================
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(QN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // K-major A and B
     if (lane == 0) q_mbar_wait(&wbar, 0);
-    for (int s = T - 1; s >= 1; --s) {
+    for (int s = T - 1, k = 0; s >= 1; --s) {
+      if (!((active >> (backwards ? (T - 1 - s) : s)) & 1ull)) continue;
       if (lane == 0) {
-        q_mbar_wait(&bready, (uint32_t)((T - 1 - s) & 1));
+        q_mbar_wait(&bready, (uint32_t)(k & 1));
         q_fence_after();
         const uint64_t b_hi0 = q_desc(q_smem(sB), 16, 1024, 2), b_lo0 = q_desc(q_smem(sB + 8192), 16, 1024, 2);
         for (int mb = 0; mb < MB; ++mb) {
@@ -593,6 +649,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       }
       __syncwarp();
       q_cluster_sync();
+      ++k;
     }
   } else {
     // ===================== 256 worker threads =====================
@@ -629,6 +686,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
     auto fetch = [&](int s) {
       const int t = backwards ? (T - 1 - s) : s;
       const int t_prev = (s == 0) ? -1 : (backwards ? t + 1 : t - 1);
+      const bool act = (active >> t) & 1ull;           // an inactive frame only needs its dout
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         pf_dout[i] = pf_c[i] = pf_cp[i] = 0.f;
@@ -637,6 +695,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         if (n_ok[i] && u_ok) {
           const size_t row = (size_t)ng[i] * T + t;
           pf_dout[i] = __ldg(dout + row * ldh + ug);
+          if (!act) continue;
           pf_g[i] = __ldg(reinterpret_cast<const float4*>(gates + row * H4 + 4 * ug));
           pf_c[i] = __ldg(cell + row * H + ug);
           pf_cp[i] = t_prev < 0 ? cell_init[ug] : __ldg(cell + ((size_t)ng[i] * T + t_prev) * H + ug);
@@ -645,9 +704,29 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       }
     };
     fetch(T - 1);
-    int par = 0;
+    int par = 0, k = 0;                                // k counts the active steps with a recurrent product (s > 0)
     for (int s = T - 1; s >= 0; --s) {
       const int t = backwards ? (T - 1 - s) : s;
+      if (!((active >> t) & 1ull)) {
+        // tile-wide masked frame: dg = 0, the hidden-state gradient collects this frame's dout and passes through
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dh_pass[i] = 0.f;
+          if (n_ok[i] && u_ok) {
+            dh_pass[i] = pf_dout[i] + dh_next[i];
+            dh_next[i] = dh_pass[i];
+            const size_t o = ((size_t)ng[i] * T + t) * H4 + 4 * ug;
+            *reinterpret_cast<float4*>(dgates + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dg_hi != nullptr) {
+              *reinterpret_cast<uint2*>(dg_hi + o) = make_uint2(0u, 0u);
+              *reinterpret_cast<uint2*>(dg_lo + o) = make_uint2(0u, 0u);
+            }
+          }
+        }
+        if (s == 0) break;
+        fetch(s - 1);
+        continue;
+      }
       // ---- 1. cell backward for my 4 cells; dg -> global (fp32) and -> the fp16 operand tile ----
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -690,7 +769,8 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(q_smem(&bready)) : "memory");
       // ---- 2./3. my k row of the partial product -> the owner's inbox ----
-      q_mbar_wait(&accbar, (uint32_t)((T - 1 - s) & 1));
+      q_mbar_wait(&accbar, (uint32_t)(k & 1));
+      ++k;
       q_fence_after();
       if (mbk < MB) {
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mbk * BCOLS);

@@ -29,7 +29,11 @@ int sm_count() {
 
 extern "C" {
 const char* ipavsr_last_error(void) { return ipavsr::g_err; }
-int ipavsr_version(void) { return 100; }
+int ipavsr_version(void) { return 200; }
+#ifndef IPAVSR_SRC_HASH
+#define IPAVSR_SRC_HASH "unknown"
+#endif
+const char* ipavsr_source_hash(void) { return IPAVSR_SRC_HASH; }
 uint64_t ipavsr_launch_count(void) { return ipavsr::g_launches.load(); }
 
 int ipavsr_device_info(int* sm, int* major, int* minor, int* max_smem_optin) {

@@ -55,10 +55,47 @@ class DevMat(object):
             (self.rows, self.cols), (self.ld, 1)) if self.rows > 0 else self.t.new_zeros((0, self.cols))
 
 
+_STAMP = [0]     # global modification counter shared by every arena (which copy of a shared parameter is the newest)
+
+
 class ParamArena(object):
     """Flat device arena for every parameter of a network + the mapping Lasagne Param <-> device view."""
 
+    @staticmethod
+    def next_stamp():
+        _STAMP[0] += 1
+        return _STAMP[0]
+
+    def stamp_of(self, p):
+        return max(self.pstamp.get(p, 0), self.stamp_all)
+
+    def touch_all(self):
+        """Every parameter of this arena was just modified on the device (an optimiser step)."""
+        self.stamp_all = self.next_stamp()
+
+    def touch(self, params):
+        st = self.next_stamp()
+        for p in params:
+            self.pstamp[p] = st
+
+    def sync_from_peers(self):
+        """Refresh every parameter another arena holds a more recently modified copy of (engines sharing parameters)."""
+        if not self.shared:
+            return
+        for p in self.shared:
+            mine = self.stamp_of(p)
+            best, best_st = None, mine
+            for a in p.arenas():
+                if a is not self and a.stamp_of(p) > best_st:
+                    best, best_st = a, a.stamp_of(p)
+            if best is not None:
+                self._view(self.flat, p).copy_(best._view(best.flat, p))
+                self.pstamp[p] = best_st
+                self.split_dirty = True
+
     def __init__(self, layer_list, device):
+        import weakref
+        self.pstamp, self.stamp_all, self.shared = {}, 0, []
         self.device = device
         self.tensors = {}      # key -> (offset, rows, cols, ld, trainable)
         self.bind = {}         # Param -> (key, index function)
@@ -134,13 +171,22 @@ class ParamArena(object):
             seg[o // SEG: o // SEG + (rows * ld + SEG - 1) // SEG] = i
         self.seg_host = seg
         self.split_dirty = True
-        # upload host masters, then bind
+        # initial values: the newest copy of every parameter (the host master, or another engine's device copy when the
+        # parameter is already bound — e.g. a function on an intermediate layer compiled after training), then bind
         params = list(self.bind.keys())
+        stamp = self.next_stamp()
         for p in params:
-            self._view(self.flat, p).copy_(torch.from_numpy(np.ascontiguousarray(p._host)).reshape(
+            self._view(self.flat, p).copy_(torch.from_numpy(np.ascontiguousarray(p.get_value())).reshape(
                 self._view(self.flat, p).shape))
+            self.pstamp[p] = max([a.stamp_of(p) for a in p.arenas()] + [0])
         for p in params:
-            p._binding = (self, p)
+            peers = p.arenas()
+            if peers:
+                self.shared.append(p)
+                for a in peers:
+                    if p not in a.shared:
+                        a.shared.append(p)
+            p._bindings.append(weakref.ref(self))
 
     # -- views ------------------------------------------------------------------------------------------
     def mat(self, key, which='flat'):
@@ -176,10 +222,11 @@ class ParamArena(object):
         buf = getattr(self, which)
         return self._view(buf, p).detach().cpu().numpy().astype(np.float32).reshape(p.shape).copy()
 
-    def write(self, p, value):
+    def write(self, p, value, stamp=None):
         self.split_dirty = True
         v = self._view(self.flat, p)
         v.copy_(torch.from_numpy(np.ascontiguousarray(value, dtype=np.float32)).reshape(v.shape))
+        self.pstamp[p] = stamp if stamp is not None else self.next_stamp()
 
     def opt_state(self, name):
         if name not in self.state:
@@ -188,6 +235,72 @@ class ParamArena(object):
 
     def tensor_of(self, p):
         return self.bind[p][0]
+
+
+class _PackPlan(object):
+    """Index tables of the packed / length-sorted execution of one padded batch (csrc/pack.cu), built on the host
+    from the utterance lengths and uploaded in one copy.
+
+    The reference zero-pads every utterance to T (`utils/datagen.py:129-139`) and encodes all N*T rows
+    (`modelzoo/pretrained_encoder.py:4-9`).  Here the encoder sees the M valid frames only, utterances sorted by
+    decreasing length, plus ONE zero row (row M) whose output is the constant every padding frame takes (SURVEY A.2);
+    everything behind the encoder runs on the padded layout in the same sorted order, which makes the utterances of
+    an LSTM tile equally long, so the recurrence kernels skip the frames at which their whole tile is masked.
+      pack[r]   (M+1)  original padded row n*T+t of packed row r; -1 for the zero row
+      valid[r]  (M)    sorted padded row of packed row r
+      unpack[q] (N*T)  packed row of sorted padded row q (M for padding frames)
+      perm[q]   (N*T)  original padded row of sorted padded row q;  unperm = its inverse
+      order[i]  (N)    original utterance of sorted utterance i;    inv = its inverse
+      mask      (N,T)  uint8, the mask in sorted order"""
+
+    def __init__(self, lens, T):
+        lens = np.asarray(lens, dtype=np.int64).reshape(-1)
+        N = len(lens)
+        self.N, self.T = N, int(T)
+        order = np.argsort(-lens, kind='stable')
+        ls = lens[order]
+        off = np.zeros(N + 1, dtype=np.int64)
+        off[1:] = np.cumsum(ls)
+        M = int(off[N])
+        self.M = M
+        utt = np.repeat(np.arange(N, dtype=np.int64), ls)
+        tt = np.arange(M, dtype=np.int64) - off[utt]
+        pack = np.empty(M + 1, dtype=np.int32)
+        pack[:M] = order[utt] * T + tt
+        pack[M] = -1
+        valid = (utt * T + tt).astype(np.int32)
+        unpack = np.full(N * T, M, dtype=np.int32)
+        unpack[valid] = np.arange(M, dtype=np.int32)
+        perm = (order[:, None] * T + np.arange(T, dtype=np.int64)[None, :]).reshape(-1).astype(np.int32)
+        unperm = np.empty(N * T, dtype=np.int32)
+        unperm[perm] = np.arange(N * T, dtype=np.int32)
+        inv = np.empty(N, dtype=np.int32)
+        inv[order] = np.arange(N, dtype=np.int32)
+        mask = (np.arange(T)[None, :] < ls[:, None]).astype(np.uint8).reshape(-1)
+        mask4 = np.zeros((N * T + 3) // 4 * 4, dtype=np.uint8)
+        mask4[:N * T] = mask
+        self.order_host, self.perm_host, self.lens_sorted, self.offsets_host = order, perm, ls, off
+        self.tables = [('pack', pack), ('valid', valid), ('unpack', unpack), ('perm', perm), ('unperm', unperm),
+                       ('order', order.astype(np.int32)), ('inv', inv), ('mask', mask4.view(np.int32))]
+        self.dev = None
+
+    def upload(self, device, pinned):
+        """One host->device copy of all tables (through the pinned staging tensor `pinned`, int32, large enough)."""
+        tot = sum(len(a) for _, a in self.tables)
+        host = pinned[:tot]
+        o = 0
+        hn = host.numpy()
+        for _, a in self.tables:
+            hn[o:o + len(a)] = a
+            o += len(a)
+        self.dev = host.to(device, non_blocking=True)
+        o = 0
+        for name, a in self.tables:
+            setattr(self, name, self.dev[o:o + len(a)])
+            o += len(a)
+        self.mask = self.mask.view(torch.uint8)[:self.N * self.T].view(self.N, self.T)
+        self.offsets = torch.from_numpy(self.offsets_host).to(device, non_blocking=True)
+        return tot
 
 
 class _Profiler(object):
@@ -227,6 +340,8 @@ class _Run(object):
         self.vals = {}
         self.saved = {}
         self.grads = {}
+        self.plan = None        # _PackPlan when the batch runs packed / length-sorted
+        self.packed = set()     # layers whose value holds the packed rows (M valid frames + the zero row)
         self.cat = {}           # ConcatLayer -> (materialised buffer, bound tensor)
         self.lstm_db_done = set()   # LSTMs whose bias gradient the backward kernel produced itself
         self.pending = {}       # layer -> CUDA event of work still running on a side stream
@@ -235,14 +350,16 @@ class _Run(object):
 
 
 class Engine(object):
-    def __init__(self, output_layer, device=None, gemm_mode=None, lstm_impl=None, delta_exact=None):
+    def __init__(self, output_layer, device=None, gemm_mode=None, lstm_impl=None, delta_exact=None, packed=None):
         if not torch.cuda.is_available():
             raise RuntimeError('ipavsr_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.out = output_layer
         self.layers = L.get_all_layers(output_layer)
-        self.gemm_mode = GEMM_MODES[gemm_mode or os.environ.get('IPAVSR_GEMM_MODE', 'fp32')]
+        # f16x3 (fp32-parity three-product arithmetic on the fp16 tensor cores + tensor-core LSTM recurrence) is the
+        # shipped default; 'fp32' (CUDA-core FFMA everywhere) is the cross-check mode
+        self.gemm_mode = GEMM_MODES[gemm_mode or os.environ.get('IPAVSR_GEMM_MODE', 'f16x3')]
         self.lstm_impl = int(os.environ.get('IPAVSR_LSTM_IMPL', '0')) if lstm_impl is None else int(lstm_impl)
         self.delta_exact = int(os.environ.get('IPAVSR_DELTA_EXACT', '1')) if delta_exact is None else int(delta_exact)
         with torch.cuda.device(self.device):
@@ -289,6 +406,35 @@ class Engine(object):
                     self.cat_plan[l] = (offs, o)
                     for i, off in zip(l.input_layers, offs):
                         self.cat_of[i] = (l, off)
+        # Packed / length-sorted execution (_PackPlan): an input that only feeds a stack of (non-softmax) DenseLayers — a
+        # DBNF encoder — is packed to its valid frames; the LAST layer of that stack expands back to the padded layout.
+        # packed: None/'auto' = when a batch has >= 1/16 padding frames and >= 2048 rows, 'force' = whenever the mask is a
+        # prefix mask (tests), 'off' = never (IPAVSR_PACKED=0).
+        self.packed_mode = packed if packed is not None else {'0': 'off', '2': 'force'}.get(
+            os.environ.get('IPAVSR_PACKED', '1'), 'auto')
+        self.pack_in, self.pack_tail = {}, {}
+        for l in self.input_layers:
+            if l in self.mask_layers:
+                continue
+            chain, c = [], l
+            while True:
+                cons = consumers.get(c, [])
+                if len(cons) != 1 or c is self.out:
+                    break
+                nxt = cons[0]
+                if isinstance(nxt, L.ReshapeLayer):
+                    c = nxt
+                elif isinstance(nxt, L.DenseLayer) and nxt.nonlinearity.name != 'softmax':
+                    chain.append(nxt)
+                    c = nxt
+                else:
+                    break
+            if chain:
+                self.pack_in[l] = chain[-1]
+                self.pack_tail[chain[-1]] = l
+        self._plans = []             # most recent _PackPlans [(key, plan)]
+        self._plan_pins = []         # ring of pinned staging tensors [(tensor, event)]
+        self._lens_cache = {}
         self.dropout_seed = 1234
         self.dropout_calls = 0
         self.world = None            # (rank, world_size, group) when data-parallel
@@ -395,6 +541,11 @@ class Engine(object):
             self._split_cache[key] = hit
         return hit[0], hit[1]
 
+    def _set_amax(self, m, t):
+        """Registers the device max|m| produced alongside `m`.  The entry holds m's storage: while it exists the
+        allocator cannot hand the same address to another buffer that would then read a stale 'ready' scale."""
+        self._amax[(m.ptr, m.rows, m.cols, m.ld)] = (t, m.t)
+
     def _const14(self):
         """[amax = 1.0, exponent = 14] for tensors bounded by 1 (sigmoid / tanh activations, LSTM hidden states)."""
         if self._c14 is None:
@@ -428,6 +579,8 @@ class Engine(object):
             hi = torch.empty(n, dtype=torch.float16, device=self.device)
             lo = torch.empty(n, dtype=torch.float16, device=self.device)
             amax = self._amax.pop(key, None)
+            if amax is not None:
+                amax = amax[0]
             ready = amax is not None
             if amax is None:
                 amax = torch.empty(2, dtype=torch.float32, device=self.device)
@@ -463,7 +616,7 @@ class Engine(object):
                         # the epilogue leaves max|C| behind, so the split of C (first use as an operand) needs no
                         # reduction pass
                         t = torch.zeros(2, dtype=torch.float32, device=self.device)
-                        self._amax[key] = t
+                        self._set_amax(Cm, t)
                         amax = t.data_ptr()
                 _lib.call('ipavsr_gemm_f16x3', transA, transB, M, N, K, ah, al, A.ld, ea, bh, bl, B.ld, eb,
                           Cm.ptr, Cm.ld, bias, act, accumulate, amax, chi, clo, 14, self.stream)
@@ -497,6 +650,103 @@ class Engine(object):
                       bias if last else None, act if last else 0, 1 if i > 0 else 0,
                       emit_split=emit_split and len(segs) == 1)
             k0 += a.cols
+
+    # ------------------------------------------------------------------------------------------------
+    # packed / length-sorted execution
+    # ------------------------------------------------------------------------------------------------
+    def _lens_of(self, mask):
+        """Utterance lengths of a PREFIX mask (host array or device tensor), or None when it is not one."""
+        if isinstance(mask, torch.Tensor) and mask.is_cuda:
+            lens = getattr(mask, '_ipavsr_lens', None)      # utils/datagen.DeviceDataset.gather knows them on the host
+            if lens is not None:
+                return np.asarray(lens, dtype=np.int64)
+            key = (mask.data_ptr(), mask._version, tuple(mask.shape))
+            if key not in self._lens_cache:
+                m = mask != 0
+                ln = m.sum(1)
+                ok = (m == (torch.arange(m.shape[1], device=m.device)[None, :] < ln[:, None])).all()
+                h = torch.cat([ln.to(torch.int64), ok.to(torch.int64).reshape(1)]).cpu().numpy()   # one host sync
+                self._lens_cache = {key: (h[:-1].copy() if h[-1] else None)}
+            return self._lens_cache[key]
+        a = np.asarray(mask) != 0
+        if a.ndim != 2:
+            return None
+        lens = a.sum(1)
+        if not (a == (np.arange(a.shape[1])[None, :] < lens[:, None])).all():
+            return None
+        return lens.astype(np.int64)
+
+    def _get_plan(self, inputs):
+        """The _PackPlan of this batch, or None when it runs in the reference's padded layout."""
+        if self.packed_mode == 'off' or len(self.mask_layers) != 1:
+            return None
+        ml = next(iter(self.mask_layers))
+        mask = inputs.get(ml)
+        if mask is None or len(mask.shape) != 2:
+            return None
+        N, T = int(mask.shape[0]), int(mask.shape[1])
+        for l in self.input_layers:        # every stream must be a (N, T, F) sequence of the same batch
+            if l is not ml and (len(inputs[l].shape) != 3 or tuple(inputs[l].shape[:2]) != (N, T)):
+                return None
+        lens = self._lens_of(mask)
+        if lens is None or N == 0:
+            return None
+        if self.packed_mode != 'force' and (N * T < 2048 or (N * T - int(lens.sum())) * 16 < N * T):
+            return None
+        key = (T, lens.tobytes())
+        for i, (k, plan) in enumerate(self._plans):
+            if k == key:
+                if i:
+                    self._plans.insert(0, self._plans.pop(i))
+                return plan
+        plan = _PackPlan(lens, T)
+        need = sum(len(a) for _, a in plan.tables)
+        # pinned staging ring: a buffer is reused only after the copy that last read it has completed
+        if len(self._plan_pins) < 4:
+            self._plan_pins.insert(0, [torch.empty(max(need, 1 << 16), dtype=torch.int32).pin_memory(), None])
+        else:
+            self._plan_pins.insert(0, self._plan_pins.pop())
+            if self._plan_pins[0][1] is not None:
+                self._plan_pins[0][1].synchronize()
+            if self._plan_pins[0][0].numel() < need:
+                self._plan_pins[0][0] = torch.empty(need, dtype=torch.int32).pin_memory()
+        if self._plan_pins[0][0].numel() < need:
+            self._plan_pins[0][0] = torch.empty(need, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(self.device):
+            plan.upload(self.device, self._plan_pins[0][0])
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        self._plan_pins[0][1] = ev
+        self._plans.insert(0, (key, plan))
+        del self._plans[8:]
+        return plan
+
+    def _gather(self, src_ptr, src_pitch, rows_out, cols, idx, keep=None, stream=None):
+        """DevMat (rows_out x cols) = rows of a float32 matrix at `src_ptr` (row pitch src_pitch floats; device memory or
+        pinned host memory) selected by the device index table `idx` (-1: zero row)."""
+        out = self.new(rows_out, cols, zero=(_ld8(cols) != cols))
+        _lib.call('ipavsr_gather_rows', src_ptr, 4 * src_pitch, out.ptr, 4 * out.ld, 4 * cols, idx.data_ptr(), None,
+                  rows_out, stream if stream is not None else self.stream)
+        return out
+
+    def _plan_input(self, plan, l, t, stream=None):
+        """Input stream `t` ((N, T, F) float32 torch tensor: device, or pinned host) in the plan's layout: packed rows for
+        an encoder input, whole utterances in sorted order otherwise."""
+        N, T, F = t.shape
+        if l in self.pack_in:
+            return self._gather(t.data_ptr(), F, plan.M + 1, F, plan.pack, stream=stream)
+        return self._gather(t.data_ptr(), F, N * T, F, plan.perm, stream=stream)
+
+    @staticmethod
+    def _as_f32_tensor(arr):
+        """(tensor, pinned-or-device flag) of an input array without copying when it already is float32 contiguous."""
+        if isinstance(arr, torch.Tensor):
+            t = arr
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(arr).astype(np.float32, copy=False)))
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(torch.float32).contiguous()
+        return t, (t.is_cuda or t.is_pinned())
 
     # ------------------------------------------------------------------------------------------------
     # input staging
@@ -543,9 +793,10 @@ class Engine(object):
 
     def prefetch(self, inputs):
         """Stage the host inputs of a later forward() now (function(...).prefetch)."""
-        staged = self._stage_inputs(inputs, allow_chunks=False)
+        plan = self._get_plan(inputs)
+        staged = self._stage_inputs(inputs, allow_chunks=False, plan=plan)
         if staged:
-            self._prefetched.append((self._host_signature(inputs, self.input_layers), staged))
+            self._prefetched.append((self._host_signature(inputs, self.input_layers), (staged, plan)))
             del self._prefetched[:-4]          # a forgotten prefetch must not pin device memory for ever
 
     def _take_prefetched(self, inputs):
@@ -581,7 +832,7 @@ class Engine(object):
             chunks.append((r0, r1 - r0, ev))
         return DevMat(d, d.data_ptr(), N * T, F, F, chunks=chunks)
 
-    def _stage_inputs(self, inputs, allow_chunks=True):
+    def _stage_inputs(self, inputs, allow_chunks=True, plan=None):
         """Host inputs are copied on a dedicated copy stream, all issued up front in graph order, so that the upload of
         the later streams overlaps the encoder of the first ones; the compute stream waits per input, on first use.
         Pinned host tensors make the copies truly asynchronous.  Returns {layer: (device value, event)}."""
@@ -600,6 +851,20 @@ class Engine(object):
         with torch.cuda.stream(cs):
             for l in order:
                 val = None
+                if plan is not None:
+                    if l in self.mask_layers:
+                        continue                    # the plan carries the (sorted) mask
+                    # pinned host memory is read by the gather kernel itself: only the valid frames of an encoder
+                    # stream cross PCIe (ragged upload); pageable memory is copied whole first
+                    t, direct = self._as_f32_tensor(inputs[l])
+                    if not direct:
+                        t = t.to(self.device, non_blocking=True)
+                    val = self._plan_input(plan, l, t, stream=C.c_void_p(cs.cuda_stream))
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    val.t.record_stream(main)
+                    staged[l] = (val, ev, t)        # t: keeps the source alive until the call consumed the staged value
+                    continue
                 if allow_chunks and l in self.chunkable and self.gemm_mode == 4 and l not in self.mask_layers:
                     val = self._upload_chunked(inputs[l], cs)
                 if val is None:
@@ -623,7 +888,14 @@ class Engine(object):
                 break
         N, T = int(first.shape[0]), int(first.shape[1])
         run = _Run(N, T)
-        staged = self._take_prefetched(inputs) or self._stage_inputs(inputs)
+        self.arena.sync_from_peers()
+        pre = self._take_prefetched(inputs)
+        if pre is not None:
+            staged, plan = pre
+        else:
+            plan = self._get_plan(inputs)
+            staged = self._stage_inputs(inputs, plan=plan)
+        run.plan = plan
         self._split_cache = {}
         self._split_by_storage = {}
         self._amax = {}
@@ -637,20 +909,36 @@ class Engine(object):
                 if i is not None and i in run.pending and not (isinstance(l, L.LSTMLayer) and i in self.mask_layers):
                     self._wait(run, i)
             if isinstance(l, L.InputLayer):
-                if l in staged:
-                    val, ev = staged[l]
+                if plan is not None and l in self.mask_layers:
+                    run.vals[l] = plan.mask                 # the mask in sorted utterance order (part of the plan)
+                elif l in staged:
+                    val, ev = staged[l][:2]
                     if not (isinstance(val, DevMat) and val.chunks):     # chunked inputs are awaited chunk by chunk
                         torch.cuda.current_stream(self.device).wait_event(ev)
                     run.vals[l] = val if l in self.mask_layers else [val]
+                    if plan is not None and l in self.pack_in:
+                        run.packed.add(l)
+                elif plan is not None:
+                    t, direct = self._as_f32_tensor(inputs[l])
+                    if not direct:
+                        t = t.to(self.device, non_blocking=True)
+                    run.vals[l] = [self._plan_input(plan, l, t)]
+                    run.keep.append(t)
+                    if l in self.pack_in:
+                        run.packed.add(l)
                 elif l in self.mask_layers:
                     run.vals[l] = self._upload(inputs[l], 'mask')
                 else:
                     run.vals[l] = [self._upload(inputs[l], 'float')]
             elif isinstance(l, L.ReshapeLayer):
                 run.vals[l] = run.vals[l.input_layer]
+                if l.input_layer in run.packed:
+                    run.packed.add(l)
             elif isinstance(l, L.DenseLayer):
                 segs = run.vals[l.input_layer]
                 rows = segs[0].rows
+                if l.input_layer in run.packed and l not in self.pack_tail:
+                    run.packed.add(l)
                 W = ar.mat((l, 'W'))
                 b = ar.mat((l, 'b')).ptr if l.b is not None else None
                 out = self.new(rows, l.num_units)
@@ -666,9 +954,17 @@ class Engine(object):
                         torch.cuda.current_stream(self.device).wait_event(ev)
                         self.gemm(x.row_slice(r0, n), W, out.row_slice(r0, n), n, out.cols, x.cols, 0, 0, b,
                                   ACT[l.nonlinearity.name], 0, amax_t=amax_t)
-                    self._amax[(out.ptr, out.rows, out.cols, out.ld)] = amax_t
+                    self._set_amax(out, amax_t)
                 else:
                     self._proj(segs, W, out, b, ACT[l.nonlinearity.name], emit_split=True)
+                if l.input_layer in run.packed and l in self.pack_tail:
+                    # last layer of a packed encoder: expand to the padded (sorted) layout; every padding frame takes the
+                    # output of the zero row, enc(0).  Backward needs the packed output.
+                    run.saved[l] = out
+                    full = self.new(N * T, l.num_units, zero=(out.ld != l.num_units))
+                    _lib.call('ipavsr_gather_rows', out.ptr, 4 * out.ld, full.ptr, 4 * full.ld, 4 * l.num_units,
+                              plan.unpack.data_ptr(), None, N * T, st)
+                    out = full
                 run.vals[l] = [out]
             elif isinstance(l, L.BatchNormLayer):
                 x = run.vals[l.input_layer][0]
@@ -691,6 +987,8 @@ class Engine(object):
                               save.data_ptr(), save.data_ptr() + 4 * F, x.rows, F, m_total, l.epsilon, l.alpha, 0,
                               1 if update_bn else 0, st)
                     run.saved[l] = (save, m_total)
+                    if update_bn:
+                        ar.touch([l.mean, l.inv_std])
                 run.vals[l] = [y]
             elif isinstance(l, L.DropoutLayer):
                 segs = run.vals[l.input_layer]
@@ -700,8 +998,10 @@ class Engine(object):
                     rows = segs[0].rows
                     tot = sum(s.cols for s in segs)
                     if dropout_masks is not None and l.name in dropout_masks:
-                        keep_full = torch.from_numpy(np.ascontiguousarray(
-                            np.asarray(dropout_masks[l.name]).reshape(rows, tot).astype(np.uint8))).to(self.device)
+                        km = np.asarray(dropout_masks[l.name]).reshape(rows, tot)
+                        if plan is not None:
+                            km = km[plan.perm_host if rows == N * T else plan.order_host]
+                        keep_full = torch.from_numpy(np.ascontiguousarray(km.astype(np.uint8))).to(self.device)
                     else:
                         keep_full = torch.empty(rows, tot, dtype=torch.uint8, device=self.device)
                         _lib.call('ipavsr_dropout_mask', keep_full.data_ptr(), rows * tot, float(l.p),
@@ -797,9 +1097,9 @@ class Engine(object):
                         # the materialised concat is bounded by the largest of its LSTMs' bounds (atomic max, same stream)
                         _lib.call('ipavsr_amax', ar.mat((l, 'hid_init')).ptr, H, 1, H, cat_bound.data_ptr(), st)
                     else:
-                        self._amax[(out.ptr, out.rows, out.cols, out.ld)] = bound
+                        self._set_amax(out, bound)
                     if hprev is not None:
-                        self._amax[(hprev.ptr, hprev.rows, hprev.cols, hprev.ld)] = bound.clone()
+                        self._set_amax(hprev, bound.clone())
             elif isinstance(l, (L.ElemwiseSumLayer, L.AdaptiveElemwiseSumLayer)):
                 ins = [self._single(run.vals[i]) for i in l.input_layers]
                 rows, F = ins[0].rows, ins[0].cols
@@ -813,7 +1113,7 @@ class Engine(object):
                 if l in run.cat:
                     cat, bound = run.cat[l]
                     if self.gemm_mode == 4:
-                        self._amax[(cat.ptr, cat.rows, cat.cols, cat.ld)] = bound
+                        self._set_amax(cat, bound)
                     run.vals[l] = [cat]
                 else:
                     segs = []
@@ -828,7 +1128,24 @@ class Engine(object):
             else:
                 raise TypeError('unsupported layer type %s' % type(l).__name__)
         self._join(run)
-        return run, run.vals[self.out]
+        outv = run.vals[self.out]
+        run.out_sorted = outv
+        if plan is not None and self.out not in run.packed:
+            # back to the caller's utterance order
+            res = []
+            for sg in outv:
+                if sg.rows == N * T:
+                    idx = plan.unperm
+                elif sg.rows == N:
+                    idx = plan.inv
+                else:
+                    raise RuntimeError('output with %d rows in a batch of %d x %d' % (sg.rows, N, T))
+                o = self.new(sg.rows, sg.cols, zero=(_ld8(sg.cols) != sg.cols))
+                _lib.call('ipavsr_gather_rows', sg.ptr, 4 * sg.ld, o.ptr, 4 * o.ld, 4 * sg.cols, idx.data_ptr(), None,
+                          sg.rows, st)
+                res.append(o)
+            outv = res
+        return run, outv
 
     def _single(self, segs):
         if len(segs) == 1:
@@ -918,13 +1235,25 @@ class Engine(object):
                     if l.b is not None:
                         _lib.call('ipavsr_colsum', dZ.ptr, dZ.ld, G((l, 'b')).ptr, rows, Nout, 0, st)
                 else:
-                    dZ = dY if run.grads[l][1] else self.new(rows, Nout)
+                    owned = run.grads[l][1]
                     y = run.vals[l][0]
+                    if l in self.pack_tail and l.input_layer in run.packed:
+                        # backward of the expansion: valid frames gather their gradient rows, the zero row collects the
+                        # gradients of all padding frames (they share its output)
+                        plan = run.plan
+                        y = run.saved[l]
+                        dYp = self.new(plan.M + 1, Nout, zero=(_ld8(Nout) != Nout))
+                        _lib.call('ipavsr_gather_rows', dY.ptr, 4 * dY.ld, dYp.ptr, 4 * dYp.ld, 4 * Nout,
+                                  plan.valid.data_ptr(), None, plan.M, st)
+                        _lib.call('ipavsr_colsum_masked', dY.ptr, dY.ld, plan.mask.data_ptr(), 1,
+                                  dYp.ptr + 4 * plan.M * dYp.ld, N * T, Nout, 0, st)
+                        dY, owned, rows = dYp, True, plan.M + 1
+                    dZ = dY if owned else self.new(rows, Nout)
                     amax = None
                     if self.gemm_mode == 4:
                         self._split_cache.pop((dZ.ptr, dZ.rows, dZ.cols, dZ.ld), None)     # dY's split (if any) is stale
                         t = torch.zeros(2, dtype=torch.float32, device=self.device)
-                        self._amax[(dZ.ptr, dZ.rows, dZ.cols, dZ.ld)] = t
+                        self._set_amax(dZ, t)
                         amax = t.data_ptr()
                     _lib.call('ipavsr_dense_bwd_prep', dY.ptr, dY.ld, y.ptr, y.ld, dZ.ptr, dZ.ld,
                               G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0,
@@ -1106,16 +1435,36 @@ class Engine(object):
     def loss_and_backward(self, run, probs, loss, y, mask, count=None):
         """Runs the loss kernel (writes loss sum into the gradient arena tail) and the full backward."""
         st, ar = self.stream, self.arena
-        p = probs[0]
+        plan = run.plan
+        # a packed / length-sorted run computes the loss in its own utterance order: targets follow, the mask is the plan's
+        p = run.out_sorted[0] if plan is not None else probs[0]
         tail = ar.grad.data_ptr() + 4 * ar.tail
         ar.grad[ar.tail: ar.tail + 4].zero_()
         if self.world is not None:
             ar.grad[ar.tail + 2: ar.tail + 3].fill_(1.0)     # sums to world_size in the gradient all-reduce
         dlogits = self.new(p.rows, p.cols)
-        yd = self._upload(y, 'int')
+        if loss == 'squared_error':
+            yd = None
+        elif plan is None:
+            yd = self._upload(y, 'int')
+        elif isinstance(y, torch.Tensor) and y.is_cuda:
+            ys = y.to(torch.int32).contiguous().view(plan.N, -1)
+            yd = torch.empty_like(ys)
+            _lib.call('ipavsr_gather_rows', ys.data_ptr(), 4 * ys.shape[1], yd.data_ptr(), 4 * ys.shape[1],
+                      4 * ys.shape[1], plan.order.data_ptr(), None, plan.N, st)
+        else:
+            yh = y.numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
+            yd = self._upload(yh[plan.order_host], 'int')
         count_dev = None
         if loss == 'temporal_softmax':
-            md = mask if isinstance(mask, torch.Tensor) and mask.is_cuda else self._upload(mask, 'mask')
+            if plan is not None:
+                if count is None and not (isinstance(mask, torch.Tensor) and mask.is_cuda):
+                    count = float(np.asarray(mask).sum())
+                if count is None:
+                    count = float(plan.M)
+                md = plan.mask
+            else:
+                md = mask if isinstance(mask, torch.Tensor) and mask.is_cuda else self._upload(mask, 'mask')
             if count is None:
                 count = float(np.asarray(mask).sum()) if not isinstance(mask, torch.Tensor) else None
             if count is None or self.world is not None:
@@ -1137,6 +1486,8 @@ class Engine(object):
         elif loss == 'squared_error':
             # T.mean(squared_error(pred, target)): mean over every element of the GLOBAL batch; dlogits is d/d(output)
             td = self._target_matrix(y, p)
+            if plan is not None:
+                td = self._gather(td.ptr, td.ld, td.rows, td.cols, plan.perm if td.rows == plan.N * plan.T else plan.order)
             n_glob = p.rows * p.cols * (self.world[1] if self.world is not None else 1)
             ar.grad[ar.tail + 1: ar.tail + 2].fill_(float(n_glob))
             _lib.call('ipavsr_squared_error', p.ptr, p.ld, td.ptr, td.ld, tail, dlogits.ptr, dlogits.ld, p.rows, p.cols,
@@ -1241,6 +1592,7 @@ class Engine(object):
     def optim_step(self, kind, lr, params=None, lr_map=None, **hp):
         ar, st = self.arena, self.stream
         ar.split_dirty = True
+        ar.touch_all()
         self._split_cache = {}
         self._split_by_storage = {}
         self._amax = {}
@@ -1307,4 +1659,17 @@ def get_engine(output_layer, **kw):
     if eng is None:
         eng = Engine(output_layer, **kw)
         output_layer._ipavsr_engine = eng
+    else:
+        have = {'gemm_mode': [k for k, v in GEMM_MODES.items() if v == eng.gemm_mode][0], 'lstm_impl': eng.lstm_impl,
+                'delta_exact': eng.delta_exact, 'packed': eng.packed_mode, 'device': str(eng.device)}
+        for k, v in kw.items():
+            if v is None:
+                continue
+            if k not in have:
+                raise TypeError('unknown engine option %r' % (k,))
+            ok = str(torch.device(v)) == have[k] if k == 'device' else (
+                int(v) == have[k] if k in ('lstm_impl', 'delta_exact') else v == have[k])
+            if not ok:
+                raise ValueError('the engine of this network already exists with %s=%r; %r was asked for'
+                                 % (k, have[k], v))
     return eng

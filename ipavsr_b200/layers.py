@@ -34,7 +34,10 @@ class Param(object):
     """A named parameter tensor with Lasagne-style tags.
 
     `value` is the host master copy until an engine binds the parameter to its device arena; afterwards
-    `get_value()` reads the device and `set_value()` writes it (see `engine.ParamArena`).
+    `get_value()` reads the device and `set_value()` writes it (see `engine.ParamArena`).  A parameter can be bound by
+    several engines (a function compiled on an intermediate layer after training, `create_pretrained_model` reusing
+    layers): every arena carries a modification stamp per parameter, `get_value()` reads the most recently modified
+    copy, `set_value()` writes all of them, and an engine refreshes its copy from a newer one before it runs.
     """
 
     def __init__(self, value, name, tags):
@@ -42,12 +45,26 @@ class Param(object):
         self.name = name
         self.tags = set(tags)
         self.shape = self._host.shape
-        self._binding = None          # (arena, slot) once bound
+        self._bindings = []           # weak references to the arenas that hold a device copy
+
+    def arenas(self):
+        live = [r() for r in self._bindings]
+        if any(a is None for a in live):
+            self._bindings = [r for r, a in zip(self._bindings, live) if a is not None]
+        return [a for a in live if a is not None]
+
+    @property
+    def _binding(self):
+        """(arena, slot) of the most recently modified device copy, or None while the parameter lives on the host."""
+        live = self.arenas()
+        if not live:
+            return None
+        return max(live, key=lambda a: a.stamp_of(self)), self
 
     def get_value(self):
-        if self._binding is not None:
-            arena, slot = self._binding
-            return arena.read(slot)
+        b = self._binding
+        if b is not None:
+            return b[0].read(self)
         return self._host.copy()
 
     def set_value(self, v):
@@ -56,9 +73,11 @@ class Param(object):
             raise ValueError('mismatch: parameter %s has shape %r but value has shape %r'
                              % (self.name, self.shape, v.shape))
         self._host = np.array(v, dtype=np.float32, order='C')
-        if self._binding is not None:
-            arena, slot = self._binding
-            arena.write(slot, self._host)
+        live = self.arenas()
+        if live:
+            stamp = live[0].next_stamp()
+            for arena in live:
+                arena.write(self, self._host, stamp=stamp)
 
     def __repr__(self):
         return self.name

@@ -79,6 +79,9 @@ class DeviceDataset(object):
                   mask.data_ptr() if mask is not None else None, yb.data_ptr() if yb is not None else None, n, T, F, _st())
         out = (X,)
         if with_mask:
+            # the lengths are known on the host: the engine's packed execution (engine._PackPlan) reads them from the mask
+            # tensor instead of synchronising with the device to recover them
+            mask._ipavsr_lens = self.seqlens_host[idx_host].copy()
             out += (mask,)
         if with_labels:
             out += (yb,)
