@@ -294,6 +294,10 @@ int ipavsr_diff_image(const float* x, int ldx, float* y, int ldy, const int64_t*
  * max_len = the longest utterance (sizes the shared-memory tile) */
 int ipavsr_deltas_fir(const float* x, int ldx, double* y, int ldy, const int64_t* offsets, int U, int F, int w,
                       int max_len, void* stream);
+/* the same array rounded once to float32 — `concat_first_second_deltas(...).astype('float32')`, the form every runner feeds
+ * the network (avletters/preprocess_images.py:20-26 writes dctFeatures, avletters/bimodal.py:351 reads them back as float32) */
+int ipavsr_deltas_fir_f32(const float* x, int ldx, float* y, int ldy, const int64_t* offsets, int U, int F, int w,
+                          int max_len, void* stream);
 
 /* ---- f3: the rest of utils/preprocessing.py on device -------------------------------- */
 /* zigzag (:280-338): order_host[i] (HOST buffer, rows*cols ints) = row-major index of the i-th element of the traversal

@@ -70,6 +70,7 @@ _SIGS = {
     'ipavsr_seq_mean_sub': (I, [P, I, P, I, P, I, I, P]),
     'ipavsr_diff_image': (I, [P, I, P, I, P, I, I, P]),
     'ipavsr_deltas_fir': (I, [P, I, P, I, P, I, I, I, I, P]),
+    'ipavsr_deltas_fir_f32': (I, [P, I, P, I, P, I, I, I, I, P]),
     'ipavsr_zigzag_indices': (I, [I, I, P]),
     'ipavsr_dct_basis': (I, [P, I, P, I, I, P]),
     'ipavsr_dct_project': (I, [P, I, P, I, P, I, I64, I, I, P]),

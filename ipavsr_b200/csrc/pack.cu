@@ -87,7 +87,15 @@ extern "C" int ipavsr_gather_rows(const void* src, int64_t src_pitch_bytes, void
   if (rows == 0) return IPAVSR_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long blocks = (rows + 7) / 8;
-  const long long cap = (long long)sm_count() * 8;
+  // A device source is an HBM-bound copy: fill the machine.  A pinned-host source is PCIe-bound (~50 GB/s needs only a
+  // few hundred KB in flight) and runs on a copy stream NEXT to the compute kernels: one CTA per SM leaves the thread
+  // slots of every SM to them (8 CTAs x 256 threads would occupy all 2048 and serialise the step behind the upload).
+  long long cap = (long long)sm_count() * 8;
+  if (src != nullptr) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) cap = sm_count();
+    else (void)cudaGetLastError();
+  }
   if (blocks > cap) blocks = cap;
   const uintptr_t all = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
                         reinterpret_cast<uintptr_t>(fill_row) | (uintptr_t)src_pitch_bytes | (uintptr_t)dst_pitch_bytes |

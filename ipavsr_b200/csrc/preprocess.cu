@@ -240,7 +240,10 @@ __global__ void __launch_bounds__(128) diff_image_kernel(const float* __restrict
 
 // ---- a13 deltas (:17-51) + concat_first_second_deltas (:465-489): float64 [x | d1 | d2] ----
 // d[t] = sum_{j=-h..h} j * X(t+j),  X(i) = x[1] for i<0 (the reference's left-pad quirk, :43), x[len-1] for i>=len.
-__global__ void __launch_bounds__(256) deltas_fir_kernel(const float* __restrict__ x, int ldx, double* __restrict__ y,
+// OUT = double: the reference's array; OUT = float: the same values rounded once, i.e. `.astype('float32')` of it, which
+// is what every runner feeds the network (avletters/bimodal.py:351 `dct_data['dctFeatures'].astype('float32')`).
+template <typename OUT>
+__global__ void __launch_bounds__(256) deltas_fir_kernel(const float* __restrict__ x, int ldx, OUT* __restrict__ y,
                                                          int ldy, const int64_t* __restrict__ offsets, int F, int h,
                                                          int max_len) {
   extern __shared__ __align__(16) double dsm[];
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256) deltas_fir_kernel(const float* __restrict
     if (lane < fc) {
       double v = (double)x[(b + t) * ldx + c0 + lane];
       s0[t * 32 + lane] = v;
-      y[(b + t) * (int64_t)ldy + c0 + lane] = v;
+      y[(b + t) * (int64_t)ldy + c0 + lane] = (OUT)v;
     }
   __syncthreads();
   const int left = len > 1 ? 1 : 0;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(256) deltas_fir_kernel(const float* __restrict
           acc += (double)j * src[i * 32 + lane];
         }
         dst[t * 32 + lane] = acc;
-        y[(b + t) * (int64_t)ldy + (pass + 1) * F + c0 + lane] = acc;
+        y[(b + t) * (int64_t)ldy + (pass + 1) * F + c0 + lane] = (OUT)acc;
       }
     __syncthreads();
   }
@@ -288,6 +291,34 @@ static inline int grid_cap(int64_t want, int per_sm) {
 }  // namespace ipavsr
 
 using namespace ipavsr;
+
+template <typename OUT>
+static int deltas_fir_launch(const float* x, int ldx, OUT* y, int ldy, const int64_t* offsets, int U, int F, int w,
+                             int max_len, void* stream, const char* fn) {
+  if (!(x && y && offsets && U >= 0 && F >= 1 && w >= 1 && max_len >= 1)) {
+    set_error("%s: bad arguments", fn);
+    return IPAVSR_ERR_ARG;
+  }
+  if (ldy < 3 * F) {
+    set_error("%s: ldy too small", fn);
+    return IPAVSR_ERR_ARG;
+  }
+  if (U == 0) return IPAVSR_OK;
+  size_t smem = (size_t)2 * max_len * 32 * sizeof(double);
+  if (smem > 200 * 1024) {
+    set_error("%s: utterance too long for the shared-memory tile (max_len <= 400)", fn);
+    return IPAVSR_ERR_ARG;
+  }
+  if (smem > 48 * 1024)
+    IPAVSR_CUDA(cudaFuncSetAttribute(deltas_fir_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int u0 = 0; u0 < U; u0 += 65535) {          // gridDim.y limit
+    const int n = U - u0 < 65535 ? U - u0 : 65535;
+    dim3 grid((F + 31) / 32, n);
+    deltas_fir_kernel<OUT><<<grid, 256, smem, S(stream)>>>(x, ldx, y, ldy, offsets + u0, F, w / 2, max_len);
+    IPAVSR_LAUNCH_CHECK();
+  }
+  return IPAVSR_OK;
+}
 
 extern "C" {
 
@@ -369,18 +400,12 @@ int ipavsr_diff_image(const float* x, int ldx, float* y, int ldy, const int64_t*
 
 int ipavsr_deltas_fir(const float* x, int ldx, double* y, int ldy, const int64_t* offsets, int U, int F, int w,
                       int max_len, void* stream) {
-  IPAVSR_CHECK_ARG(x && y && offsets && U >= 0 && F >= 1 && w >= 1 && max_len >= 1, "bad arguments");
-  IPAVSR_CHECK_ARG(ldy >= 3 * F, "ldy too small");
-  if (U == 0) return IPAVSR_OK;
-  IPAVSR_CHECK_ARG(U <= 65535, "at most 65535 utterances per call");
-  size_t smem = (size_t)2 * max_len * 32 * sizeof(double);
-  IPAVSR_CHECK_ARG(smem <= 200 * 1024, "utterance too long for the shared-memory tile (max_len <= 400)");
-  if (smem > 48 * 1024)
-    IPAVSR_CUDA(cudaFuncSetAttribute(deltas_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((F + 31) / 32, U);
-  deltas_fir_kernel<<<grid, 256, smem, S(stream)>>>(x, ldx, y, ldy, offsets, F, w / 2, max_len);
-  IPAVSR_LAUNCH_CHECK();
-  return IPAVSR_OK;
+  return deltas_fir_launch<double>(x, ldx, y, ldy, offsets, U, F, w, max_len, stream, "ipavsr_deltas_fir");
+}
+
+int ipavsr_deltas_fir_f32(const float* x, int ldx, float* y, int ldy, const int64_t* offsets, int U, int F, int w,
+                          int max_len, void* stream) {
+  return deltas_fir_launch<float>(x, ldx, y, ldy, offsets, U, F, w, max_len, stream, "ipavsr_deltas_fir_f32");
 }
 
 }  // extern "C"

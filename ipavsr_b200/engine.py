@@ -23,6 +23,7 @@ import torch
 
 from . import _lib
 from . import layers as L
+from .derived import Derived, DiffImages, DctFeatures
 
 ACT = {'linear': 0, 'sigmoid': 1, 'rectify': 2, 'tanh': 3, 'leaky_rectify': 4, 'very_leaky_rectify': 5,
        'softplus': 6, 'elu': 7}
@@ -432,6 +433,7 @@ class Engine(object):
             if chain:
                 self.pack_in[l] = chain[-1]
                 self.pack_tail[chain[-1]] = l
+        self._dct_basis = {}         # (image shape, K) -> DCT basis of a derived DCT stream
         self._plans = []             # most recent _PackPlans [(key, plan)]
         self._plan_pins = []         # ring of pinned staging tensors [(tensor, event)]
         self._lens_cache = {}
@@ -666,8 +668,10 @@ class Engine(object):
                 ln = m.sum(1)
                 ok = (m == (torch.arange(m.shape[1], device=m.device)[None, :] < ln[:, None])).all()
                 h = torch.cat([ln.to(torch.int64), ok.to(torch.int64).reshape(1)]).cpu().numpy()   # one host sync
-                self._lens_cache = {key: (h[:-1].copy() if h[-1] else None)}
-            return self._lens_cache[key]
+                if len(self._lens_cache) >= 32:
+                    self._lens_cache.clear()
+                self._lens_cache[key] = (h[:-1].copy() if h[-1] else None, mask)    # holds the tensor: the address stays its own
+            return self._lens_cache[key][0]
         a = np.asarray(mask) != 0
         if a.ndim != 2:
             return None
@@ -678,20 +682,25 @@ class Engine(object):
 
     def _get_plan(self, inputs):
         """The _PackPlan of this batch, or None when it runs in the reference's padded layout."""
-        if self.packed_mode == 'off' or len(self.mask_layers) != 1:
+        if len(self.mask_layers) != 1 or (self.packed_mode == 'off' and not any(
+                isinstance(v, Derived) for v in inputs.values())):
             return None
         ml = next(iter(self.mask_layers))
         mask = inputs.get(ml)
         if mask is None or len(mask.shape) != 2:
             return None
         N, T = int(mask.shape[0]), int(mask.shape[1])
+        derived = False
         for l in self.input_layers:        # every stream must be a (N, T, F) sequence of the same batch
-            if l is not ml and (len(inputs[l].shape) != 3 or tuple(inputs[l].shape[:2]) != (N, T)):
+            if isinstance(inputs[l], Derived):
+                derived = True             # computed on the device from the packed frames of its source: needs the plan
+            elif l is not ml and (len(inputs[l].shape) != 3 or tuple(inputs[l].shape[:2]) != (N, T)):
                 return None
         lens = self._lens_of(mask)
         if lens is None or N == 0:
             return None
-        if self.packed_mode != 'force' and (N * T < 2048 or (N * T - int(lens.sum())) * 16 < N * T):
+        if (self.packed_mode != 'force' and not derived and
+                (N * T < 2048 or (N * T - int(lens.sum())) * 16 < N * T)):
             return None
         key = (T, lens.tobytes())
         for i, (k, plan) in enumerate(self._plans):
@@ -782,6 +791,9 @@ class Engine(object):
         sig = []
         for l in layers:
             a = inputs[l]
+            if isinstance(a, Derived):
+                sig.append((id(l), id(a.source), type(a).__name__))
+                continue
             if isinstance(a, torch.Tensor):
                 if a.is_cuda:
                     continue
@@ -837,7 +849,7 @@ class Engine(object):
         the later streams overlaps the encoder of the first ones; the compute stream waits per input, on first use.
         Pinned host tensors make the copies truly asynchronous.  Returns {layer: (device value, event)}."""
         host = [l for l in self.input_layers
-                if not (isinstance(inputs[l], torch.Tensor) and inputs[l].is_cuda)]
+                if not (isinstance(inputs[l], torch.Tensor) and inputs[l].is_cuda) and not isinstance(inputs[l], Derived)]
         if not host or os.environ.get('IPAVSR_COPY_STREAM', '1') == '0':
             return {}
         if self._copy_stream is None:
@@ -875,6 +887,107 @@ class Engine(object):
                 staged[l] = (val, ev)
         return staged
 
+    def _input(self, run, l, inputs, staged):
+        """Value of InputLayer `l` for this run (memoised in run.vals): staged host copy, device tensor, the plan's mask, or a
+        stream derived on the device from another input (derived.py)."""
+        plan = run.plan
+        N, T = run.N, run.T
+        a = inputs[l]
+        if isinstance(a, Derived):
+            if plan is None:
+                raise ValueError('a derived input stream needs the utterance lengths: pass a prefix mask (one mask input)')
+            run.vals[l] = [self._derive(run, l, a, inputs, staged)]
+        elif plan is not None and l in self.mask_layers:
+            run.vals[l] = plan.mask                 # the mask in sorted utterance order (part of the plan)
+        elif l in staged:
+            val, ev = staged[l][:2]
+            if not (isinstance(val, DevMat) and val.chunks):     # chunked inputs are awaited chunk by chunk
+                torch.cuda.current_stream(self.device).wait_event(ev)
+            run.vals[l] = val if l in self.mask_layers else [val]
+            if plan is not None and l in self.pack_in:
+                run.packed.add(l)
+        elif plan is not None:
+            t, direct = self._as_f32_tensor(a)
+            if not direct:
+                t = t.to(self.device, non_blocking=True)
+            run.vals[l] = [self._plan_input(plan, l, t)]
+            run.keep.append(t)
+            if l in self.pack_in:
+                run.packed.add(l)
+        elif l in self.mask_layers:
+            run.vals[l] = self._upload(a, 'mask')
+        else:
+            run.vals[l] = [self._upload(a, 'float')]
+        return run.vals[l]
+
+    def _packed_rows(self, run, l, inputs, staged):
+        """The M valid frames (+ the zero row) of input stream `l` in the plan's sorted order."""
+        plan = run.plan
+        if l not in run.vals:
+            self._input(run, l, inputs, staged)
+        v = run.vals[l][0]
+        if l in run.packed:
+            return v
+        key = ('packed', l)
+        if key not in run.saved:
+            out = self.new(plan.M + 1, v.cols, zero=(_ld8(v.cols) != v.cols))
+            _lib.call('ipavsr_gather_rows', v.ptr, 4 * v.ld, out.ptr, 4 * out.ld, 4 * v.cols, plan.valid.data_ptr(), None,
+                      plan.M, self.stream)
+            _lib.call('ipavsr_fill', out.ptr + 4 * plan.M * out.ld, out.ld, 0.0, self.stream)     # row M: the zero row
+            run.saved[key] = out
+        return run.saved[key]
+
+    def _derive(self, run, l, spec, inputs, staged):
+        """Computes a derived stream (derived.py) on the packed frames of its source and returns it in the layout `l` takes:
+        packed rows for an encoder input, the padded sorted layout (zero padding) otherwise."""
+        plan, st = run.plan, self.stream
+        src_layer = None
+        for cand in self.input_layers:
+            if cand is not l and inputs[cand] is spec.source:
+                src_layer = cand
+        if src_layer is None or isinstance(inputs[src_layer], Derived):
+            raise ValueError('the source of a derived stream must be the array passed for another input of the same call')
+        x = self._packed_rows(run, src_layer, inputs, staged)
+        M, N = plan.M, plan.N
+        if isinstance(spec, DiffImages):
+            y = self.new(M + 1, x.cols, zero=(_ld8(x.cols) != x.cols))
+            _lib.call('ipavsr_diff_image', x.ptr, x.ld, y.ptr, y.ld, plan.offsets.data_ptr(), N, x.cols, st)
+        elif isinstance(spec, DctFeatures):
+            D, K = x.cols, spec.no_coeff
+            if spec.image_shape[0] * spec.image_shape[1] != D:
+                raise ValueError('cannot reshape frames of %d pixels into %r' % (D, spec.image_shape))
+            key = (spec.image_shape, K)
+            if key not in self._dct_basis:
+                from .utils.preprocessing import zigzag_order
+                cols = torch.from_numpy(np.ascontiguousarray(zigzag_order(*spec.image_shape)[1:K + 1],
+                                                             dtype=np.int32)).to(self.device)
+                ldb = (K + 3) // 4 * 4
+                basis = torch.empty(D, ldb, dtype=torch.float32, device=self.device)
+                _lib.call('ipavsr_dct_basis', basis.data_ptr(), ldb, cols.data_ptr(), D, K, st)
+                self._dct_basis[key] = (basis, ldb)
+            basis, ldb = self._dct_basis[key]
+            c = self.new(M + 1, K, zero=(_ld8(K) != K))
+            for f0 in range(0, M, 65535 * 128):
+                n = min(65535 * 128, M - f0)
+                _lib.call('ipavsr_dct_project', x.ptr + 4 * x.ld * f0, x.ld, basis.data_ptr(), ldb, c.ptr + 4 * c.ld * f0,
+                          c.ld, n, D, K, st)
+            if spec.deltas:
+                y = self.new(M + 1, 3 * K, zero=(_ld8(3 * K) != 3 * K))
+                _lib.call('ipavsr_deltas_fir_f32', c.ptr, c.ld, y.ptr, y.ld, plan.offsets.data_ptr(), N, K, spec.window,
+                          max(int(plan.lens_sorted.max()), 1), st)
+            else:
+                y = c
+        else:
+            raise TypeError('unknown derived stream %r' % (type(spec).__name__,))
+        _lib.call('ipavsr_fill', y.ptr + 4 * M * y.ld, y.ld, 0.0, st)        # the zero row (no utterance owns it)
+        if l in self.pack_in:
+            run.packed.add(l)
+            return y
+        full = self.new(N * run.T, y.cols, zero=(_ld8(y.cols) != y.cols))
+        _lib.call('ipavsr_gather_rows', y.ptr, 4 * y.ld, full.ptr, 4 * full.ld, 4 * y.cols, plan.unpack.data_ptr(), None,
+                  N * run.T, st)
+        return full
+
     # ------------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------------
@@ -883,7 +996,7 @@ class Engine(object):
         lib, st = self.lib, self.stream
         first = None
         for l in self.input_layers:
-            if l not in self.mask_layers:
+            if l not in self.mask_layers and not isinstance(inputs[l], Derived):
                 first = inputs[l]
                 break
         N, T = int(first.shape[0]), int(first.shape[1])
@@ -909,27 +1022,8 @@ class Engine(object):
                 if i is not None and i in run.pending and not (isinstance(l, L.LSTMLayer) and i in self.mask_layers):
                     self._wait(run, i)
             if isinstance(l, L.InputLayer):
-                if plan is not None and l in self.mask_layers:
-                    run.vals[l] = plan.mask                 # the mask in sorted utterance order (part of the plan)
-                elif l in staged:
-                    val, ev = staged[l][:2]
-                    if not (isinstance(val, DevMat) and val.chunks):     # chunked inputs are awaited chunk by chunk
-                        torch.cuda.current_stream(self.device).wait_event(ev)
-                    run.vals[l] = val if l in self.mask_layers else [val]
-                    if plan is not None and l in self.pack_in:
-                        run.packed.add(l)
-                elif plan is not None:
-                    t, direct = self._as_f32_tensor(inputs[l])
-                    if not direct:
-                        t = t.to(self.device, non_blocking=True)
-                    run.vals[l] = [self._plan_input(plan, l, t)]
-                    run.keep.append(t)
-                    if l in self.pack_in:
-                        run.packed.add(l)
-                elif l in self.mask_layers:
-                    run.vals[l] = self._upload(inputs[l], 'mask')
-                else:
-                    run.vals[l] = [self._upload(inputs[l], 'float')]
+                if l not in run.vals:
+                    self._input(run, l, inputs, staged)
             elif isinstance(l, L.ReshapeLayer):
                 run.vals[l] = run.vals[l.input_layer]
                 if l.input_layer in run.packed:
@@ -1004,8 +1098,11 @@ class Engine(object):
                         keep_full = torch.from_numpy(np.ascontiguousarray(km.astype(np.uint8))).to(self.device)
                     else:
                         keep_full = torch.empty(rows, tot, dtype=torch.uint8, device=self.device)
+                        # data-parallel shards draw from different streams (rank mixed into the seed): the masks of the
+                        # global batch are then independent, as in the single-process step
                         _lib.call('ipavsr_dropout_mask', keep_full.data_ptr(), rows * tot, float(l.p),
-                                  self.dropout_seed, self.dropout_calls << 32, st)
+                                  self.dropout_seed + 7919 * (self.world[0] if self.world is not None else 0),
+                                  self.dropout_calls << 32, st)
                         self.dropout_calls += 1
                     scale = 1.0 / (1.0 - l.p) if l.rescale else 1.0
                     outs, keeps, c0 = [], [], 0
@@ -1231,6 +1328,9 @@ class Engine(object):
                 xin = run.vals[l.input_layer]
                 rows, Nout = dY.rows, l.num_units
                 if l.nonlinearity.name == 'softmax':
+                    if l is not head:
+                        raise ValueError('softmax DenseLayer %r is not the network head: its gradient is only defined '
+                                         'through the fused loss kernels' % (l.name,))
                     dZ = dY          # the loss kernel already went through the softmax
                     if l.b is not None:
                         _lib.call('ipavsr_colsum', dZ.ptr, dZ.ld, G((l, 'b')).ptr, rows, Nout, 0, st)
@@ -1635,6 +1735,12 @@ class Engine(object):
             if k in per_tensor and per_tensor[k] != float(v):
                 raise ValueError('parameters sharing the device tensor %r need one learning rate' % (k,))
             per_tensor[k] = float(v)
+        # the four gate matrices of an LSTM (and the three peephole vectors) live in one device tensor: updating only
+        # some of them is not expressible with a per-tensor rate
+        for p, (k, idx) in ar.bind.items():
+            if idx != 'aux' and k in per_tensor and p not in lr_map and 'trainable' in p.tags and per_tensor[k] != 0.0:
+                raise ValueError('parameter %s shares the device tensor of updated parameters but is not in the update list'
+                                 % (p.name,))
         ids = np.zeros(ar.n // SEG + 1, dtype=np.int32)
         lrs = np.zeros(len(ar.order) + 1, dtype=np.float32)
         for i, k in enumerate(ar.order):

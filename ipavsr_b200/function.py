@@ -131,6 +131,25 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
     if is_loss and loss_name is None:
         raise TypeError('wrap categorical_crossentropy(...) / squared_error(...) in T.mean(...)')
     l2 = outputs.l2 if is_loss else 0.0
+    subset = None
+    if train:
+        # Theano derives the updates from THEIR loss and THEIR parameter list (`lasagne.updates.adam(cost, params, lr)`):
+        # the gradients here come from `outputs`, so the two must be the same expression, and a parameter list that is
+        # not the full trainable set becomes a per-tensor learning-rate table (absent tensors: rate 0, as in adam_vlr)
+        ul = updates.loss
+        same = ul is outputs or (is_loss and ul.kind == outputs.kind and ul.pred.layer is outputs.pred.layer and
+                                 ul.pred.deterministic == outputs.pred.deterministic and ul.targets is outputs.targets and
+                                 ul.mask is outputs.mask and ul.l2 == outputs.l2)
+        if not same:
+            raise ValueError('the updates were built from a different loss expression than the function output: the step '
+                             'would silently ignore it (pass the same cost to both)')
+        if updates.lr_map is None and updates.params is not None:
+            every = L.get_all_params(pred.layer, trainable=True)
+            unknown = [p for p in updates.params if p not in every]
+            if unknown:
+                raise ValueError('parameters %r are not trainable parameters of this network' % (unknown,))
+            if set(updates.params) != set(every):
+                subset = list(updates.params)
 
     def fn(*args, **kw):
         if len(args) != len(slots):
@@ -167,7 +186,9 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
             eng.l2_penalty(l2)
         eng.allreduce_grads()
         u = updates
-        eng.optim_step(u.kind, _lr_value(u.lr) if u.lr is not None else 0.0, params=u.params, lr_map=u.lr_map, **u.hp)
+        lr = _lr_value(u.lr) if u.lr is not None else 0.0
+        lr_map = u.lr_map if subset is None else {p: lr for p in subset}
+        eng.optim_step(u.kind, lr, params=u.params, lr_map=lr_map, **u.hp)
         return eng.read_loss()
 
     def prefetch(*args, **kw):

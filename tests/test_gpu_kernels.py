@@ -267,7 +267,11 @@ def test_lstm_fwd_tensor_core(N, T, H, peep, backwards):
     G.call('ipavsr_lstm_fwd', d_xw.data_ptr(), d_w32.data_ptr(), G.ptr(d_peep), d_ci.data_ptr(), d_hi.data_ptr(),
            d_mask.data_ptr(), e_out.data_ptr(), e_gates.data_ptr(), e_cell.data_ptr(), e_hprev.data_ptr(), N, T, H, ldh,
            int(backwards), 0, ws.data_ptr(), nbytes, G.stream())
-    for a, b, name in ((d_gates, e_gates, 'gates'), (d_cell, e_cell, 'cell'), (d_hprev, e_hprev, 'hprev'), (d_out, e_out, 'out')):
+    # the gate activations of a masked step are never read (the state passes through); the tensor-core kernel does not
+    # compute them at frames where its whole 32-utterance tile is masked, so they are compared at unmasked steps only
+    live = mask.reshape(-1).astype(bool)
+    assert G.relerr(G.host(d_gates)[live], G.host(e_gates)[live]) < tol, 'gates'
+    for a, b, name in ((d_cell, e_cell, 'cell'), (d_hprev, e_hprev, 'hprev'), (d_out, e_out, 'out')):
         assert G.relerr(G.host(a), G.host(b)) < tol, name
 
 

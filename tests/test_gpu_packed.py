@@ -278,3 +278,78 @@ def test_packed_pinned_host_inputs_and_prefetch():
     ref2 = OracleNet(net, np.float64).forward(dict(feed, mask=m2), win, deterministic=True)
     got2 = val(feed['input'], m2, feed['dct'], win)
     assert np.abs(got2 - ref2).max() / np.abs(ref2).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------
+# derived streams: diff images and DCT(+deltas) computed on the device from the raw stream's packed frames
+# ---------------------------------------------------------------------------------------------------------
+def _derived_host(raw, lens, image_shape, K):
+    """The reference's host pipeline on the valid frames, padded back: compute_diff_images (runners/3stream.py:95-96);
+    compute_dct_features + concat_first_second_deltas, float32 (avletters/preprocess_images.py:20-21, bimodal.py:351)."""
+    from oracle import preprocessing as OP
+    N, T_, D = raw.shape
+    packed = np.concatenate([raw[i, :lens[i]] for i in range(N)], 0)
+    diff_p = OP.compute_diff_images(packed, lens)
+    dct_p = OP.concat_first_second_deltas(OP.compute_dct_features(packed, image_shape, K, 'zigzag'), lens).astype('float32')
+    diff = np.zeros((N, T_, D), 'float32')
+    dct = np.zeros((N, T_, 3 * K), 'float32')
+    o = 0
+    for i in range(N):
+        diff[i, :lens[i]] = diff_p[o:o + lens[i]]
+        dct[i, :lens[i]] = dct_p[o:o + lens[i]]
+        o += lens[i]
+    return diff, dct
+
+
+@pytest.mark.parametrize('device_raw', [False, True])
+def test_derived_streams_match_host_preprocessing(device_raw):
+    from ipavsr_b200 import modelzoo, init
+    from ipavsr_b200.function import function, tensor as T
+    from ipavsr_b200.derived import DiffImages, DctFeatures
+    rng = np.random.default_rng(31)
+    np.random.seed(31)
+    ish, K, H, C, win, N, T_ = (6, 8), 5, 12, 7, 3, 40, 14
+    D = ish[0] * ish[1]
+    aes = [MU.ae_tuple(rng, d) for d in (D, D, 3 * K)]
+    v = [T.tensor3('s%d' % i) for i in range(3)]
+    m = T.matrix('mask', dtype='uint8')
+    net, _ = modelzoo.adenet_3stream.create_model(aes[0], aes[1], aes[2], (None, None, D), v[0], (None, None, D), v[1],
+                                                  (None, None, 3 * K), v[2], (None, None), m, H, win, C, 'concat',
+                                                  init.Orthogonal(), True)
+    MU.randomize_params(net, rng)
+    lens = rng.integers(2, T_ + 1, size=N)
+    lens[5] = T_
+    (raw,), mask, _ = MU.make_feed(rng, N, T_, [D], lens=lens)
+    diff, dct = _derived_host(raw, lens, ish, K)
+    val = function([v[0], v[1], v[2], m, T.iscalar('w')], L.get_output(net, deterministic=True))
+    want = val(raw, diff, dct, mask, win)
+    ref = OracleNet(net, np.float64).forward({'s1_im': raw, 's2_im': diff, 's3_im': dct, 'mask': mask}, win,
+                                             deterministic=True)
+    assert np.abs(want - ref).max() / np.abs(ref).max() < 1e-4
+    r = torch.from_numpy(raw).cuda() if device_raw else torch.from_numpy(raw).pin_memory()
+    got = val(r, DiffImages(r), DctFeatures(r, ish, K), mask, win)
+    # the diff images are bit-exact, the DCT projection carries float32 accumulation error (2e-5 of the largest coefficient)
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-4, np.abs(got - want).max()
+    assert (got.argmax(-1) == ref.argmax(-1)).all()
+    # prefetch with derived streams: only the raw stream is staged
+    if not device_raw:
+        args = (r, DiffImages(r), DctFeatures(r, ish, K), torch.from_numpy(mask).pin_memory(), win)
+        val.prefetch(*args)
+        got2 = val(*args)
+        np.testing.assert_array_equal(got2, got)
+    # training through derived streams == training on the host-computed streams
+    from ipavsr_b200.custom.objectives import temporal_softmax_loss
+    from ipavsr_b200.custom.updates import sgd
+    tg = T.imatrix('t')
+    cost = temporal_softmax_loss(L.get_output(net, deterministic=False), tg, m)
+    params = L.get_all_params(net, trainable=True)
+    train = function([v[0], v[1], v[2], tg, m, T.iscalar('w')], cost, updates=sgd(cost, params, learning_rate=0.0))
+    y = np.repeat(rng.integers(0, C, size=(N, 1)), T_, 1).astype('int32')
+    la = train(raw, diff, dct, y, mask, win)
+    ga = train.engine.param_grads(params)
+    lb = train(r, DiffImages(r), DctFeatures(r, ish, K), y, mask, win)
+    gb = train.engine.param_grads(params)
+    assert abs(la - lb) < 1e-4 * abs(la)
+    gmax = max(np.abs(g).max() for g in ga)
+    for p, a, b in zip(params, ga, gb):
+        assert np.abs(a - b).max() < 2e-3 * max(np.abs(a).max(), 2e-2 * gmax), p.name
