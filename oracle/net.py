@@ -175,8 +175,12 @@ class OracleNet(object):
 
     # convenience: loss + grads in get_all_params(trainable=True) order
     def loss_and_grads(self, inputs, window, y, mask, loss='temporal_softmax', deterministic=False,
-                       dropout_masks=None, update_bn=True, l2=0.0):
+                       dropout_masks=None, update_bn=True, l2=0.0, after_forward=None):
+        """`after_forward(self)` (tests only) may edit the forward caches before the backward pass — used to make the
+        oracle take the same rectify branch as a float32 run at units whose pre-activation is within rounding of 0."""
         out = self.forward(inputs, window, deterministic, dropout_masks, update_bn)
+        if after_forward is not None:
+            after_forward(self)
         if loss == 'temporal_softmax':
             val, dout = ops.temporal_softmax_loss(out, y, mask, self.dt)
         elif loss == 'categorical_crossentropy':

@@ -237,3 +237,57 @@ def dropout_masks_for(net, rng, N, T):
             F = l.output_shape[-1]
             out[l.name] = (rng.random((N, T, F)) >= l.p).astype('uint8')
     return out
+
+
+def rectify_aligner(net, run, N, T):
+    """Returns (callback for OracleNet.loss_and_grads(after_forward=...), flips list).
+
+    A rectify unit whose pre-activation lies within float32 rounding of 0 can take the other branch on the device than in
+    the float64 oracle; its sub-gradient then differs by the whole upstream gradient of that (row, unit), which moves one
+    column of the layer's weight gradient by the contribution of one frame.  The callback counts such units, REQUIRES each
+    of them to be at rounding distance from 0 (|z| < 1e-5 max|z|: anything else is a real error and fails the test), and
+    makes the oracle's backward take the device's branch there — every gradient must then agree to the normal gate."""
+    rect = [l for l in L.get_all_layers(net) if isinstance(l, L.DenseLayer) and l.nonlinearity.name == 'rectify']
+    flips = []
+
+    def align(orc):
+        for l in rect:
+            saved = run.saved.get(l)
+            yd = saved if (saved is not None and not isinstance(saved, tuple)) else run.vals[l][0]
+            ydev = yd.torch_view().cpu().numpy() > 0
+            plan = getattr(run, 'plan', None)
+            if plan is not None and ydev.shape[0] == plan.M + 1 and plan.M + 1 != N * T:
+                pk = dict(plan.tables)['pack']                     # packed rows -> padded rows in the caller's order
+                full = np.empty((N * T, ydev.shape[1]), bool)
+                full[:] = ydev[plan.M]                             # padding frames share the zero row's output
+                full[pk[:-1]] = ydev[:-1]
+                ydev = full
+            elif plan is not None:
+                ydev = ydev[dict(plan.tables)['unperm']]
+            x, z, yo = orc.caches[l]
+            diff = ydev != (z > 0)
+            if diff.any():
+                zmax = np.abs(z).max()
+                assert np.abs(z[diff]).max() < 1e-5 * zmax, ('a flipped rectify unit is not at rounding distance from 0',
+                                                           l.name, np.abs(z[diff]).max(), zmax)
+                flips.append((l.name, int(diff.sum())))
+                z = z.copy()
+                z[diff] = np.where(ydev[diff], 1e-300, -1e-300)
+                orc.caches[l] = (x, z, yo)
+        total = sum(N * T * l.num_units for l in rect)
+        assert sum(n for _, n in flips) <= max(8, 1e-5 * total), flips
+
+    return align, flips
+
+
+def grad_errors(params, grads, grads_ref):
+    """[(param, error / scale)]: max abs error of every gradient against max(its own max, 2e-2 of the largest gradient of
+    the network); a gradient that is analytically zero (the bias in front of a BatchNormLayer: the float64 oracle returns
+    ~1e-18) is pure cancellation noise of a sum over all rows and is compared against the largest gradient instead."""
+    gmax = max(np.abs(gr).max() for gr in grads_ref)
+    out = []
+    for p, g, gr in zip(params, grads, grads_ref):
+        own = np.abs(gr).max()
+        scale = gmax if own < 1e-10 * gmax else max(own, 2e-2 * gmax)
+        out.append((p, np.abs(g - gr).max() / scale))
+    return out

@@ -47,42 +47,52 @@ def _fusions(name):
     return ['sum', 'adasum', 'concat'] if name in ('adenet_v2', 'adenet_v3', 'adenet_3stream', 'adenet_4stream') else ['sum']
 
 
+# gradient gate of the small-network sweeps: GRAD_TOL of the per-tensor max (analytically-zero gradients against the scale
+# of the others).  SURVEY 8(d) asks for 1e-4; the measured worst case over all builders, fusion types and both modes is
+# printed by the tests (-s) and recorded in profiles/.
+GRAD_TOL = 1e-4
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'f16x3'])
 @pytest.mark.parametrize('name', MU.ALL)
-def test_forward_backward_parity(name):
-    _check_forward_backward(name, _fusions(name))
+def test_forward_backward_parity(name, mode):
+    """Every builder in the CUDA-core cross-check mode and in the shipped default (f16x3 + tensor-core LSTM; at these toy
+    sizes the GEMMs below the tensor-core threshold run the exact FP32 kernel, the recurrences run on the tensor cores)."""
+    _check_forward_backward(name, _fusions(name), mode)
 
 
-def _check_forward_backward(name, fusiontypes):
+def _check_forward_backward(name, fusiontypes, mode='fp32'):
     for fusiontype in fusiontypes:
         spec, net, feed, mask, y, dm, win = _case(name, _seed(name), fusiontype)
-        loss_ref, out_ref, grads_ref = _oracle(net, feed, win, y, mask, spec['level'], dm)
-        eng = Engine(net, gemm_mode='fp32')
+        eng = Engine(net, gemm_mode=mode)
         ins = MU.input_layers(net)
         dfeed = {ins[k]: v for k, v in feed.items()}
         run, out = eng.forward(dfeed, win, deterministic=False, train=True, dropout_masks=dm, update_bn=False)
+        # the oracle's backward takes the device's branch at rectify units within rounding of 0 (counted, and required to
+        # be at rounding distance: model_util.rectify_aligner)
+        align, flips = MU.rectify_aligner(net, run, mask.shape[0], mask.shape[1])
+        loss_name = 'categorical_crossentropy' if spec['level'] == 'seq' else 'temporal_softmax'
+        loss_ref, out_ref, grads_ref = OracleNet(net, np.float64).loss_and_grads(
+            feed, win, y, mask, loss_name, deterministic=False, dropout_masks=dm, update_bn=False, after_forward=align)
         probs = eng.read(out).reshape(out_ref.shape)
         rel = np.abs(probs - out_ref).max() / np.abs(out_ref).max()
         assert rel < 1e-4, (name, fusiontype, 'probs', rel)
         assert (probs.argmax(-1) == out_ref.argmax(-1)).all()
-        loss_name = 'categorical_crossentropy' if spec['level'] == 'seq' else 'temporal_softmax'
         eng.loss_and_backward(run, out, loss_name, y, mask, count=float(mask.sum()))
         loss = eng.read_loss()
         assert abs(loss - loss_ref) < 1e-4 * abs(loss_ref), (name, loss, loss_ref)
         params = L.get_all_params(net, trainable=True)
-        grads = eng.param_grads(params)
-        gmax = max(np.abs(gr).max() for gr in grads_ref)
-        for p, g, gr in zip(params, grads, grads_ref):
-            # a gradient that is analytically zero (e.g. the bottleneck bias in front of BatchNorm) is compared
-            # against the scale of the other gradients, not against its own rounding noise
-            scale = max(np.abs(gr).max(), 2e-2 * gmax)
-            err = np.abs(g - gr).max() / scale
-            assert err < 2e-3, (name, fusiontype, p.name, err, scale)
+        errs = MU.grad_errors(params, eng.param_grads(params), grads_ref)
+        for p, err in errs:
+            assert err < GRAD_TOL, (name, fusiontype, mode, p.name, err, flips)
+        print('PARITY %s %s %s: probs rel %.2e, worst grad err %.2e, rectify flips %s'
+              % (name, fusiontype, mode, rel, max(e for _, e in errs), flips))
 
 
 @pytest.mark.parametrize('mode', ['f16x3', 'tf32x3'])
 def test_tensor_core_modes_at_reference_sizes(mode):
     """The fp32-parity tensor-core GEMM modes on the real layer sizes (D=1200, DBNF 2000-1000-500-50, DCT 90, LSTM-250,
-    26 classes, T=40): same gates as the CUDA-core fp32 mode — probabilities 1e-4, identical argmax, gradients 2e-3."""
+    26 classes, T=40): same gates as the CUDA-core fp32 mode — probabilities 1e-4, identical argmax, gradients 1e-4."""
     from ipavsr_b200 import modelzoo, init
     rng = np.random.default_rng(77)
     np.random.seed(77)
@@ -109,15 +119,11 @@ def test_tensor_core_modes_at_reference_sizes(mode):
     eng.loss_and_backward(run, out, 'temporal_softmax', y, mask, count=float(mask.sum()))
     assert abs(eng.read_loss() - loss_ref) < 1e-4 * abs(loss_ref)
     params = L.get_all_params(net, trainable=True)
-    grads = eng.param_grads(params)
-    gmax = max(np.abs(gr).max() for gr in grads_ref)
-    worst = 0.0
-    for p, g, gr in zip(params, grads, grads_ref):
-        scale = max(np.abs(gr).max(), 2e-2 * gmax)
-        err = np.abs(g - gr).max() / scale
-        worst = max(worst, err)
-        assert err < 2e-3, (mode, p.name, err, scale)
-    print('mode %s: probs rel %.2e, worst grad err %.2e' % (mode, rel, worst))
+    errs = MU.grad_errors(params, eng.param_grads(params), grads_ref)
+    for p, err in errs:
+        assert err < GRAD_TOL, (mode, p.name, err)
+    print('PARITY adenet_v2 concat N=24 reference sizes, mode %s: probs rel %.2e, worst grad err %.2e'
+          % (mode, rel, max(e for _, e in errs)))
 
 
 def test_deterministic_eval_and_val_fn_api():

@@ -217,7 +217,7 @@ def _run(net, feed, win, y, mask, level, dm, mode, packed, device_inputs=False):
     yy = torch.from_numpy(y).cuda() if device_inputs else y
     eng.loss_and_backward(run, out, loss_name, yy, dfeed[ins['mask']], count=float(mask.sum()))
     params = L.get_all_params(net, trainable=True)
-    return probs, float(eng.read_loss()), eng.param_grads(params), params
+    return probs, float(eng.read_loss()), eng.param_grads(params), params, run
 
 
 @pytest.mark.parametrize('name,fusiontype,device_inputs',
@@ -229,27 +229,28 @@ def _run(net, feed, win, y, mask, level, dm, mode, packed, device_inputs=False):
 def test_packed_run_matches_padded_run_and_oracle(name, fusiontype, device_inputs, mode):
     spec, net, feed, mask, y, dm, win = _case(name, 21, fusiontype, N=41, T=13)
     level = spec['level']
-    p0, l0, g0, params = _run(net, feed, win, y, mask, level, dm, mode, 'off')
-    p1, l1, g1, _ = _run(net, feed, win, y, mask, level, dm, mode, 'force', device_inputs)
-    # the two layouts differ only in summation order (and in the utterances an LSTM tile groups together)
-    assert np.abs(p1 - p0).max() < 2e-5 * np.abs(p0).max(), np.abs(p1 - p0).max()
-    assert abs(l1 - l0) < 2e-5 * abs(l0)
-    gmax = max(np.abs(g).max() for g in g0)
-    for p, a, b in zip(params, g1, g0):
-        scale = max(np.abs(b).max(), 2e-2 * gmax)
-        assert np.abs(a - b).max() / scale < 2e-4, (p.name, np.abs(a - b).max() / scale)
-    # and against the float64 oracle (original utterance order)
+    p0, l0, g0, params, _ = _run(net, feed, win, y, mask, level, dm, mode, 'off')
+    p1, l1, g1, _, run1 = _run(net, feed, win, y, mask, level, dm, mode, 'force', device_inputs)
+    # against the float64 oracle (original utterance order); rectify branches at rounding distance from 0 follow the
+    # device (model_util.rectify_aligner)
     lname = 'categorical_crossentropy' if level == 'seq' else 'temporal_softmax'
-    loss_ref, out_ref, grads_ref = OracleNet(net, np.float64).loss_and_grads(feed, win, y, mask, lname, deterministic=False,
-                                                                            dropout_masks=dm, update_bn=False)
+    align, flips = MU.rectify_aligner(net, run1, 41, 13)
+    loss_ref, out_ref, grads_ref = OracleNet(net, np.float64).loss_and_grads(
+        feed, win, y, mask, lname, deterministic=False, dropout_masks=dm, update_bn=False, after_forward=align)
     pr = p1.reshape(out_ref.shape)
     assert np.abs(pr - out_ref).max() / np.abs(out_ref).max() < 1e-4
     assert (pr.argmax(-1) == out_ref.argmax(-1)).all()
     assert abs(l1 - loss_ref) < 1e-4 * abs(loss_ref)
-    gmax = max(np.abs(g).max() for g in grads_ref)
-    for p, a, b in zip(params, g1, grads_ref):
-        scale = max(np.abs(b).max(), 2e-2 * gmax)
-        assert np.abs(a - b).max() / scale < 2e-3, (p.name, np.abs(a - b).max() / scale)
+    for p, err in MU.grad_errors(params, g1, grads_ref):
+        assert err < 1e-4, (p.name, err, flips)
+    # the two layouts differ only in summation order (and in the utterances an LSTM tile groups together); a rectify unit at
+    # rounding distance from 0 may still take different branches in the two runs, so the direct comparison is made when
+    # the oracle saw no such unit
+    assert np.abs(p1 - p0).max() < 2e-5 * np.abs(p0).max(), np.abs(p1 - p0).max()
+    assert abs(l1 - l0) < 2e-5 * abs(l0)
+    if not flips:
+        for p, err in MU.grad_errors(params, g1, g0):
+            assert err < 1e-4, (p.name, err)
 
 
 def test_packed_pinned_host_inputs_and_prefetch():
@@ -350,6 +351,5 @@ def test_derived_streams_match_host_preprocessing(device_raw):
     lb = train(r, DiffImages(r), DctFeatures(r, ish, K), y, mask, win)
     gb = train.engine.param_grads(params)
     assert abs(la - lb) < 1e-4 * abs(la)
-    gmax = max(np.abs(g).max() for g in ga)
-    for p, a, b in zip(params, ga, gb):
-        assert np.abs(a - b).max() < 2e-3 * max(np.abs(a).max(), 2e-2 * gmax), p.name
+    for p, err in MU.grad_errors(params, gb, ga):
+        assert err < 1e-3, (p.name, err)          # the derived DCT projection carries float32 accumulation error (2e-5)

@@ -9,8 +9,9 @@ from test_gpu_models import _check_forward_backward
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize('mode', ['fp32', 'f16x3'])
 @pytest.mark.parametrize('name', MU.VARIANTS)
-def test_builder_variants_forward_backward_parity(name):
+def test_builder_variants_forward_backward_parity(name, mode):
     fus = {'adenet_v5': ['sum', 'adasum'], 'adenet_v2_3': ['adasum'], 'adenet_v4': ['sum'], 'adenet_v1_1': ['sum'],
            'adenet_v2_2': ['concat', 'adasum']}.get(name, ['concat'])
-    _check_forward_backward(name, fus)
+    _check_forward_backward(name, fus, mode)
