@@ -171,6 +171,27 @@ int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* w
                         float* db, uint16_t* dg_hi, uint16_t* dg_lo, int32_t* dg_exp, void* workspace,
                         uint64_t workspace_bytes, void* stream);
 int ipavsr_lstm_bwd_f16_supported(int N, int T, int H, int ldw, float clip);
+/* Wide layers (H > 256: adenet_v3's 2 x lstm_size = 500 LSTMs, modelzoo/adenet_v3.py:114-156; adenet_v1's second BLSTM,
+ * modelzoo/adenet_v1.py:95), whose W_hid does not fit a cluster's shared memory: the same recurrence with ONE fp16
+ * three-product tensor-core GEMM + one cell kernel per time step, all enqueued by this call (csrc/lstm_steps_tc.cu).
+ * Arguments as ipavsr_lstm_fwd_f16 / ipavsr_lstm_bwd_f16 plus the float32 w_hid (steps with fewer than 4 active rows use
+ * the exact CUDA-core product) and `active_rows` (HOST array of T ints or NULL): active_rows[t] = number of leading
+ * utterances that can be unmasked at frame t — with length-sorted batches the step GEMMs then skip the finished ones.
+ * The backward REQUIRES dg_hi/dg_lo/dg_exp (dense (N*T, 4H) halves): they are the operand of its recurrent product and
+ * the fp16 split of dgates for the weight-gradient GEMMs that follow. */
+int ipavsr_lstm_steps_supported(int N, int T, int H, int ldw);
+uint64_t ipavsr_lstm_steps_workspace_bytes(int N, int T, int H);
+int ipavsr_lstm_fwd_f16_steps(const float* xw, const float* w_hid, const uint16_t* whid_hi, const uint16_t* whid_lo,
+                              const int32_t* whid_exp, int ldw, const float* peep, const float* cell_init,
+                              const float* hid_init, const uint8_t* mask, float* out, float* gates, float* cell,
+                              float* hprev, int N, int T, int H, int ldh, int backwards, const int32_t* active_rows,
+                              void* workspace, uint64_t workspace_bytes, void* stream);
+int ipavsr_lstm_bwd_f16_steps(const float* dout, const float* w_hid, const uint16_t* whid_hi, const uint16_t* whid_lo,
+                              const int32_t* whid_exp, int ldw, const float* peep, const float* cell_init,
+                              const uint8_t* mask, const float* gates, const float* cell, float* dgates, float* dpeep,
+                              float* dcell_init, float* dhid_init, int N, int T, int H, int ldh, int backwards, float clip,
+                              int accumulate, uint16_t* dg_hi, uint16_t* dg_lo, int32_t* dg_exp,
+                              const int32_t* active_rows, void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* ---- a4/a5/a7: fusion, merge, slice, dropout ---------------------------------------------------------- */
 /* out[M,F] = sum_s coeff_s * in_s[M,F]   (ElemwiseSumLayer; AdaptiveElemwiseSumLayer custom/layers.py:178-228).

@@ -58,6 +58,11 @@ _SIGS = {
     'ipavsr_bn_fwd': (I, [P, I, P, I, P, P, P, P, P, P, P, I, I, I64, F, F, I, I, P]),
     'ipavsr_bn_bwd_stats': (I, [P, I, P, I, P, P, P, I, I, P]),
     'ipavsr_bn_bwd': (I, [P, I, P, I, P, P, P, P, P, I, P, P, I, I, I64, I, P]),
+    'ipavsr_lstm_steps_supported': (I, [I, I, I, I]),
+    'ipavsr_lstm_steps_workspace_bytes': (U64, [I, I, I]),
+    'ipavsr_lstm_fwd_f16_steps': (I, [P, P, P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, I, I, P, P, U64, P]),
+    'ipavsr_lstm_bwd_f16_steps': (I, [P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, I, I, I, I, I, F, I, P, P, P, P, P, U64,
+                                      P]),
     'ipavsr_softmax': (I, [P, I, P, I, I, I, P]),
     'ipavsr_temporal_softmax_loss': (I, [P, I, P, P, P, P, I, I, I, F, P, P]),
     'ipavsr_categorical_crossentropy': (I, [P, I, P, P, P, I, I, I, F, P, P]),

@@ -281,6 +281,8 @@ class _PackPlan(object):
         mask4 = np.zeros((N * T + 3) // 4 * 4, dtype=np.uint8)
         mask4[:N * T] = mask
         self.order_host, self.perm_host, self.lens_sorted, self.offsets_host = order, perm, ls, off
+        # active_rows[t] = number of (sorted) utterances longer than t: the rows a per-step recurrent GEMM has to compute
+        self.active_rows = np.ascontiguousarray((ls[None, :] > np.arange(T)[:, None]).sum(1).astype(np.int32))
         self.tables = [('pack', pack), ('valid', valid), ('unpack', unpack), ('perm', perm), ('unperm', unperm),
                        ('order', order.astype(np.int32)), ('inv', inv), ('mask', mask4.view(np.int32))]
         self.dev = None
@@ -1171,6 +1173,18 @@ class Engine(object):
                               ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
                               gates.ptr if gates else None, cell.ptr if cell else None, hprev.ptr if hprev else None,
                               N, T, H, out.ld, 1 if l.backwards else 0, sh)
+                elif (self.gemm_mode == 4 and self.lstm_impl == 0 and H > 256 and
+                      lib.ipavsr_lstm_steps_supported(N, T, H, whid.ld)):
+                    # wide layers (H = 500): one tensor-core GEMM + one cell kernel per time step (csrc/lstm_steps_tc.cu)
+                    wh, wl, we = self._split16(whid)
+                    sbytes = int(lib.ipavsr_lstm_steps_workspace_bytes(N, T, H))
+                    sws = torch.empty((sbytes + 3) // 4, dtype=torch.float32, device=self.device)
+                    run.keep.append(sws)
+                    act = plan.active_rows.ctypes.data_as(C.c_void_p) if plan is not None else None
+                    _lib.call('ipavsr_lstm_fwd_f16_steps', xw.ptr, whid.ptr, wh, wl, we, whid.ld, peep,
+                              ar.mat((l, 'cell_init')).ptr, ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
+                              gates.ptr if gates else None, cell.ptr if cell else None, hprev.ptr if hprev else None,
+                              N, T, H, out.ld, 1 if l.backwards else 0, act, sws.data_ptr(), sbytes, sh)
                 else:
                     _lib.call('ipavsr_lstm_fwd', xw.ptr, whid.ptr, peep, ar.mat((l, 'cell_init')).ptr,
                               ar.mat((l, 'hid_init')).ptr, mask.data_ptr(), out.ptr,
@@ -1482,7 +1496,26 @@ class Engine(object):
             ws = self._workspace(nbytes)
         clip = l.grad_clipping if l.grad_clipping else 0.0
         whid = ar.mat((l, 'W_hid'))
-        if (self.gemm_mode == 4 and self.lstm_impl == 0 and
+        steps = (self.gemm_mode == 4 and self.lstm_impl == 0 and H > 256 and 0.0 < clip < 16384.0 and
+                 not lib.ipavsr_lstm_bwd_f16_supported(N, T, H, whid.ld, float(clip)) and
+                 lib.ipavsr_lstm_steps_supported(N, T, H, whid.ld) and dG.ld == 4 * H)
+        if steps:
+            wh, wl, we = self._split16(whid)
+            n = max(dG.rows * dG.ld, 8)
+            ghi = torch.empty(n, dtype=torch.float16, device=self.device)
+            glo = torch.empty(n, dtype=torch.float16, device=self.device)
+            gex = torch.zeros(2, dtype=torch.float32, device=self.device)
+            self._split_cache[(dG.ptr, dG.rows, dG.cols, dG.ld)] = (ghi, glo, gex, dG.t)
+            self._split_by_storage.setdefault(id(dG.t), []).append((dG.ptr, dG.rows, dG.cols, dG.ld))
+            sbytes = int(lib.ipavsr_lstm_steps_workspace_bytes(N, T, H))
+            sws = torch.empty((sbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            run.keep.append(sws)
+            act = run.plan.active_rows.ctypes.data_as(C.c_void_p) if run.plan is not None else None
+            _lib.call('ipavsr_lstm_bwd_f16_steps', dout.ptr, whid.ptr, wh, wl, we, whid.ld, peep,
+                      ar.mat((l, 'cell_init')).ptr, mask.data_ptr(), gates.ptr, cell.ptr, dG.ptr, dpeep,
+                      G((l, 'cell_init')).ptr, G((l, 'hid_init')).ptr, N, T, H, dout.ld, 1 if l.backwards else 0, clip, 0,
+                      ghi.data_ptr(), glo.data_ptr(), gex.data_ptr() + 4, act, sws.data_ptr(), sbytes, stream_handle)
+        elif (self.gemm_mode == 4 and self.lstm_impl == 0 and
                 lib.ipavsr_lstm_bwd_f16_supported(N, T, H, whid.ld, float(clip))):
             wh, wl, we = self._split16(whid)
             # by-products of the kernel: the bias gradient and the fp16 split of dgates (dense 4H-wide rows)

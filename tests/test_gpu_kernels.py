@@ -720,3 +720,75 @@ def test_lstm_drift_expanding_recurrence():
           'float32 %.2e of max|h|; tensor-core first 5 steps %.2e, last 5 steps %.2e' % (d_tc, d_ff, d_np, early, late))
     assert d_tc < 1e-3 and d_ff < 1e-3
     assert d_tc < 4 * max(d_ff, d_np) + 1e-6
+
+
+@pytest.mark.parametrize('N,T,H,peep,backwards,sorted_lens', [(64, 20, 500, True, False, True), (64, 20, 500, False, True, True),
+                                                               (48, 12, 320, True, True, False), (26, 40, 500, True, False, True),
+                                                               (70, 9, 512, True, False, False)])
+def test_lstm_steps_tensor_core(N, T, H, peep, backwards, sorted_lens):
+    """ipavsr_lstm_{fwd,bwd}_f16_steps (wide layers: one tensor-core GEMM + one cell kernel per step) == the oracle, with and
+    without the per-frame active-row counts of a length-sorted batch (tails of fewer than 4 rows take the exact product)."""
+    rng = np.random.default_rng(N + T + H)
+    lens = rng.integers(1, T + 1, size=N)
+    lens[0] = T
+    if sorted_lens:
+        lens = np.sort(lens)[::-1].copy()
+    I = 12
+    p, x, mask = _lstm_inputs(rng, N, T, I, H, peep, lens)
+    p['W_hid'] = (p['W_hid'] * 0.2).astype('float32')          # non-expanding recurrence (see the drift test)
+    dout = rng.normal(size=(N, T, H)).astype('float32')
+    out_ref, cache = ops.lstm_fwd(x, mask, p, backwards, np.float64)
+    dx_ref, gr = ops.lstm_bwd(dout, cache, 5.0, np.float64)
+    xw = (x.reshape(N * T, I).astype(np.float64) @ p['W_in'].astype(np.float64) + p['b']).astype('float32')
+    ldh, ldw = (H + 7) // 8 * 8, 4 * H
+    d_xw = G.dev(G.interleave_gates(xw, H))
+    d_whid = G.dev(G.interleave_gates(p['W_hid'], H))
+    wh, wl, sc = G.zeros((H, ldw), torch.float16), G.zeros((H, ldw), torch.float16), G.zeros((2,))
+    G.call('ipavsr_f16_split', d_whid.data_ptr(), ldw, H, 4 * H, wh.data_ptr(), wl.data_ptr(), ldw, sc.data_ptr(),
+           sc.data_ptr() + 4, 0, G.stream())
+    d_peep = G.dev(p['peep']) if peep else None
+    d_ci, d_hi, d_mask = G.dev(p['cell_init']), G.dev(p['hid_init']), G.dev(mask)
+    nan = float('nan')
+    d_out = torch.full((N * T, ldh), nan, dtype=torch.float32, device='cuda')
+    d_gates = torch.full((N * T, 4 * H), nan, dtype=torch.float32, device='cuda')
+    d_cell = torch.full((N * T, H), nan, dtype=torch.float32, device='cuda')
+    d_hprev = torch.full((N * T, ldh), nan, dtype=torch.float32, device='cuda')
+    assert G.lib().ipavsr_lstm_steps_supported(N, T, H, ldw)
+    nbytes = G.lib().ipavsr_lstm_steps_workspace_bytes(N, T, H)
+    ws = G.zeros(((nbytes + 3) // 4,))
+    act = np.ascontiguousarray((lens[None, :] > np.arange(T)[:, None]).sum(1).astype(np.int32)) if sorted_lens else None
+    import ctypes as C
+    actp = act.ctypes.data_as(C.c_void_p) if act is not None else None
+    G.call('ipavsr_lstm_fwd_f16_steps', d_xw.data_ptr(), d_whid.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4, ldw,
+           G.ptr(d_peep), d_ci.data_ptr(), d_hi.data_ptr(), d_mask.data_ptr(), d_out.data_ptr(), d_gates.data_ptr(),
+           d_cell.data_ptr(), d_hprev.data_ptr(), N, T, H, ldh, int(backwards), actp, ws.data_ptr(), nbytes, G.stream())
+    out = G.host(d_out)[:, :H].reshape(N, T, H)
+    assert np.isfinite(out).all()
+    assert G.relerr(out, out_ref) < 2e-5, G.relerr(out, out_ref)
+    dop = np.zeros((N * T, ldh), 'float32')
+    dop[:, :H] = dout.reshape(N * T, H)
+    d_dout = G.dev(dop)
+    d_dg = torch.full((N * T, 4 * H), nan, dtype=torch.float32, device='cuda')
+    d_dpeep = G.zeros((3, H)) if peep else None
+    d_dci, d_dhi = G.zeros((H,)), G.zeros((H,))
+    dgh = torch.full((N * T, 4 * H), nan, dtype=torch.float16, device='cuda')
+    dgl = torch.full((N * T, 4 * H), nan, dtype=torch.float16, device='cuda')
+    dge = G.zeros((1,), torch.int32)
+    G.call('ipavsr_lstm_bwd_f16_steps', d_dout.data_ptr(), d_whid.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4,
+           ldw, G.ptr(d_peep), d_ci.data_ptr(), d_mask.data_ptr(), d_gates.data_ptr(), d_cell.data_ptr(), d_dg.data_ptr(),
+           G.ptr(d_dpeep), d_dci.data_ptr(), d_dhi.data_ptr(), N, T, H, ldh, int(backwards), 5.0, 0, dgh.data_ptr(),
+           dgl.data_ptr(), dge.data_ptr(), actp, ws.data_ptr(), nbytes, G.stream())
+    dgv = G.host(d_dg).astype(np.float64)
+    assert np.isfinite(dgv).all()
+    ex = int(G.host(dge)[0])
+    rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / 2048.0) / 2.0 ** ex
+    assert np.abs(rec - dgv).max() <= max(np.abs(dgv).max() * 2.0 ** -20, 1e-12)
+    dG = G.deinterleave_gates(G.host(d_dg), H).astype(np.float64)
+    tol = 3e-4
+    assert G.relerr(dG.sum(0), gr['b']) < tol
+    assert G.relerr((dG @ p['W_in'].astype(np.float64).T).reshape(N, T, I), dx_ref) < tol
+    assert G.relerr(G.host(d_hprev)[:, :H].astype(np.float64).T @ dG, gr['W_hid']) < tol
+    assert G.relerr(G.host(d_dci), gr['cell_init']) < tol, G.relerr(G.host(d_dci), gr['cell_init'])
+    assert G.relerr(G.host(d_dhi), gr['hid_init']) < tol, G.relerr(G.host(d_dhi), gr['hid_init'])
+    if peep:
+        assert G.relerr(G.host(d_dpeep), gr['peep']) < tol
