@@ -111,6 +111,14 @@ int ipavsr_gemm_f16_supported(int M, int N, int K, const void* A, int lda, const
  * dZ may alias dY.  db may be NULL.  amax (optional, device float, atomically max-combined) receives max |dZ|. */
 int ipavsr_dense_bwd_prep(const float* dY, int lddy, const float* Y, int ldy, float* dZ, int lddz,
                           float* db, int M, int N, int act, int accumulate_db, float* amax, void* stream);
+/* The same step for the fp16 three-product mode in ONE pass: dZ leaves only as the fp16 hi/lo pair (leading dimension ldo
+ * halves) + its scale exponent, with db; `bound` (device float) is an upper bound of max|dY| left by the producer (the
+ * dgrad GEMM's amax_out, or ipavsr_amax): |act'| <= 1, so |dZ| <= bound and no max pass over dZ is needed. */
+int ipavsr_dense_bwd_prep_f16(const float* dY, int lddy, const float* Y, int ldy, float* db, int M, int N, int act,
+                              int accumulate_db, const float* bound, uint16_t* dZ_hi, uint16_t* dZ_lo, int ldo,
+                              int32_t* exp_out, void* stream);
+int ipavsr_dense_bwd_prep_f16_supported(const float* dY, int lddy, const float* Y, int ldy, int N, const void* hi,
+                                        const void* lo, int ldo);
 /* out[N] (+)= column sums of X[M,N] */
 int ipavsr_colsum(const float* X, int ldx, float* out, int M, int N, int accumulate, void* stream);
 

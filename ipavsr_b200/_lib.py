@@ -36,6 +36,8 @@ _SIGS = {
     'ipavsr_gemm_f16x3': (I, [I, I, I, I, I, P, P, I, P, P, P, I, P, P, I, P, I, I, P, P, P, I, P]),
     'ipavsr_gemm_f16_supported': (I, [I, I, I, P, I, P, I]),
     'ipavsr_dense_bwd_prep': (I, [P, I, P, I, P, I, P, I, I, I, I, P, P]),
+    'ipavsr_dense_bwd_prep_f16': (I, [P, I, P, I, P, I, I, I, I, P, P, P, I, P, P]),
+    'ipavsr_dense_bwd_prep_f16_supported': (I, [P, I, P, I, I, P, P, I]),
     'ipavsr_colsum': (I, [P, I, P, I, I, I, P]),
     'ipavsr_delta_fwd': (I, [P, I, P, I, I, I, I, I, I, P]),
     'ipavsr_delta_bwd': (I, [P, I, P, I, I, I, I, I, I, P]),

@@ -1,6 +1,7 @@
 // Memory-bound kernels of the hot path: DenseLayer backward prep, column sums, fusion (sum / adasum / concat),
 // slice, dropout, BatchNorm, softmax + losses, fused optimiser step, TF32 split.  All are coalesced streaming
 // kernels judged by HBM GB/s; grids are sized from the SM count.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace ipavsr {
@@ -82,6 +83,66 @@ __global__ void __launch_bounds__(256) colsum_prep_vec_kernel(const float* __res
   if (amax != nullptr) {
     mx = warp_max(mx);
     if (lane == 0 && mx > 0.f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(mx));
+  }
+  if (db == nullptr) return;
+  red[rl][lane] = s;
+  __syncthreads();
+  if (rl == 0 && c < N) {
+    float4 t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 v = red[i][lane];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    atomicAdd(db + c, t.x);
+    atomicAdd(db + c + 1, t.y);
+    atomicAdd(db + c + 2, t.z);
+    atomicAdd(db + c + 3, t.w);
+  }
+}
+
+// Fused form for the fp16 three-product GEMM mode: dZ = dY * act'(Y) leaves the kernel ONLY as the fp16 hi/lo operand pair
+// the weight-gradient and data-gradient GEMMs read (gemm_tc.cu, f16split.cu), together with the bias gradient.  The scale
+// comes from an upper bound of |dY| the producer left behind (the dgrad GEMM's epilogue |C|max): |act'| <= 1 for every
+// nonlinearity of custom/nonlinearities.py, so |dZ| <= bound and one pass suffices — no float32 dZ, no max pass, no split
+// pass (12 bytes per element instead of 28).
+__global__ void __launch_bounds__(256) prep_f16_kernel(const float* __restrict__ dY, int lddy, const float* __restrict__ Y,
+                                                       int ldy, float* __restrict__ db, int M, int N, int act,
+                                                       const float* __restrict__ bound, __half* __restrict__ hi,
+                                                       __half* __restrict__ lo, int ldo, int32_t* __restrict__ exp_out) {
+  __shared__ float4 red[8][33];
+  const float b = __ldg(bound);
+  int e = 0;
+  if (b > 0.f && !isinf(b)) {
+    e = 14 - ilogbf(b);
+    e = e < -126 ? -126 : (e > 126 ? 126 : e);
+  }
+  const int e1 = e / 2, e2 = e - e1;
+  const float s1 = __int_as_float((127 + e1) << 23), s2 = __int_as_float((127 + e2) << 23);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *exp_out = e;
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * PREP_ROWS;
+  const int r1 = min(M, r0 + PREP_ROWS);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < N) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float4 g = __ldcs(reinterpret_cast<const float4*>(dY + (size_t)r * lddy + c));
+      const float4 y = __ldcs(reinterpret_cast<const float4*>(Y + (size_t)r * ldy + c));
+      g.x *= act_grad_from_y(y.x, act); g.y *= act_grad_from_y(y.y, act);
+      g.z *= act_grad_from_y(y.z, act); g.w *= act_grad_from_y(y.w, act);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+      const float v[4] = {g.x * s1 * s2, g.y * s1 * s2, g.z * s1 * s2, g.w * s1 * s2};
+      __half h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        h[k] = __float2half_rn(v[k]);
+        l[k] = __float2half_rn((v[k] - __half2float(h[k])) * 2048.0f);
+      }
+      *reinterpret_cast<uint2*>(hi + (size_t)r * ldo + c) = *reinterpret_cast<const uint2*>(h);
+      *reinterpret_cast<uint2*>(lo + (size_t)r * ldo + c) = *reinterpret_cast<const uint2*>(l);
+    }
   }
   if (db == nullptr) return;
   red[rl][lane] = s;
@@ -525,6 +586,27 @@ int ipavsr_dense_bwd_prep(const float* dY, int lddy, const float* Y, int ldy, fl
   }
   dim3 grid((N + 31) / 32, (M + PREP_ROWS - 1) / PREP_ROWS);
   colsum_prep_kernel<true><<<grid, 256, 0, S(stream)>>>(dY, lddy, Y, ldy, dZ, lddz, db, M, N, act, amax);
+  IPAVSR_LAUNCH_CHECK();
+  return IPAVSR_OK;
+}
+
+int ipavsr_dense_bwd_prep_f16_supported(const float* dY, int lddy, const float* Y, int ldy, int N, const void* hi,
+                                        const void* lo, int ldo) {
+  return (N % 4 == 0 && lddy % 4 == 0 && ldy % 4 == 0 && ldo % 4 == 0 && ldo >= N && aligned16(dY) && aligned16(Y) &&
+          (reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0) ? 1 : 0;
+}
+
+int ipavsr_dense_bwd_prep_f16(const float* dY, int lddy, const float* Y, int ldy, float* db, int M, int N, int act,
+                              int accumulate_db, const float* bound, uint16_t* dZ_hi, uint16_t* dZ_lo, int ldo,
+                              int32_t* exp_out, void* stream) {
+  IPAVSR_CHECK_ARG(M >= 0 && N >= 0 && dY && Y && bound && dZ_hi && dZ_lo && exp_out, "bad arguments");
+  IPAVSR_CHECK_ARG(ipavsr_dense_bwd_prep_f16_supported(dY, lddy, Y, ldy, N, dZ_hi, dZ_lo, ldo),
+                   "needs N % 4 == 0, leading dimensions % 4 == 0 and 16-byte aligned rows");
+  if (M == 0 || N == 0) return IPAVSR_OK;
+  if (db && !accumulate_db) IPAVSR_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, S(stream)));
+  dim3 grid((N + 127) / 128, (M + PREP_ROWS - 1) / PREP_ROWS);
+  prep_f16_kernel<<<grid, 256, 0, S(stream)>>>(dY, lddy, Y, ldy, db, M, N, act, bound, reinterpret_cast<__half*>(dZ_hi),
+                                               reinterpret_cast<__half*>(dZ_lo), ldo, exp_out);
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }

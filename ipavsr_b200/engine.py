@@ -435,6 +435,16 @@ class Engine(object):
             if chain:
                 self.pack_in[l] = chain[-1]
                 self.pack_tail[chain[-1]] = l
+        # data parallel: the gradient all-reduce is issued in buckets while the backward walk is still running — the arena
+        # is laid out in layer order and the walk finalises it from the tail (head, aggregate LSTMs, last stream ...) to
+        # the front (first encoder), so every finished range [lo, hi) can go out while the encoders' weight gradients are
+        # still being computed.  IPAVSR_AR_OVERLAP=0 restores the single all-reduce after the backward.
+        self.ar_overlap = os.environ.get('IPAVSR_AR_OVERLAP', '1') != '0'
+        self.ar_bucket_floats = int(os.environ.get('IPAVSR_AR_BUCKET', str(2 << 20)))
+        self._ar_works, self._ar_hi = [], None
+        self._layer_lo = {}
+        for key, (off, rows, cols, ld) in self.arena.tensors.items():
+            self._layer_lo[key[0]] = min(self._layer_lo.get(key[0], off), off)
         self._dct_basis = {}         # (image shape, K) -> DCT basis of a derived DCT stream
         self._plans = []             # most recent _PackPlans [(key, plan)]
         self._plan_pins = []         # ring of pinned staging tensors [(tensor, event)]
@@ -459,6 +469,8 @@ class Engine(object):
         # fp16 hi/lo of sigmoid/tanh outputs written by the GEMM epilogue itself (static scale 2^14, coalesced through the
         # epilogue's staging tile): saves the separate split pass over those activations (IPAVSR_EPILOGUE_SPLIT=0 disables)
         self.epilogue_split = os.environ.get('IPAVSR_EPILOGUE_SPLIT', '1') == '1'
+        # DenseLayer backward prep emits dZ only as the fp16 operand pair (no float32 dZ, no max / split pass over it)
+        self.fuse_prep = os.environ.get('IPAVSR_FUSE_PREP', '1') == '1'
 
     # ------------------------------------------------------------------------------------------------
     # small helpers
@@ -1321,6 +1333,8 @@ class Engine(object):
         if not softmax_head and not (isinstance(head, L.DenseLayer) and head.nonlinearity.name != 'softmax'):
             raise ValueError('a squared-error objective needs a non-softmax DenseLayer output')
         run.grads[head] = ([dlogits], True)
+        self._ar_works, self._ar_hi = [], (ar.flat.numel() if (self.world is not None and self.ar_overlap and
+                                                                getattr(self, '_ar_enabled', True)) else None)
         # number of not-yet-processed consumers of every layer: when it reaches zero the layer's gradient is final and
         # an LSTM recurrence can be launched ahead of the walk on a side stream
         remaining = {}
@@ -1362,16 +1376,43 @@ class Engine(object):
                         _lib.call('ipavsr_colsum_masked', dY.ptr, dY.ld, plan.mask.data_ptr(), 1,
                                   dYp.ptr + 4 * plan.M * dYp.ld, N * T, Nout, 0, st)
                         dY, owned, rows = dYp, True, plan.M + 1
-                    dZ = dY if owned else self.new(rows, Nout)
-                    amax = None
-                    if self.gemm_mode == 4:
-                        self._split_cache.pop((dZ.ptr, dZ.rows, dZ.cols, dZ.ld), None)     # dY's split (if any) is stale
-                        t = torch.zeros(2, dtype=torch.float32, device=self.device)
-                        self._set_amax(dZ, t)
-                        amax = t.data_ptr()
-                    _lib.call('ipavsr_dense_bwd_prep', dY.ptr, dY.ld, y.ptr, y.ld, dZ.ptr, dZ.ld,
-                              G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0,
-                              amax, st)
+                    need_dx = self.requires_grad.get(l.input_layer, False)
+                    fused = (self.gemm_mode == 4 and self.fuse_prep and not any(a.chunks for a in xin) and
+                             lib.ipavsr_dense_bwd_prep_f16_supported(dY.ptr, dY.ld, y.ptr, y.ld, Nout, 16, 16, dY.ld) and
+                             all(lib.ipavsr_gemm_f16_supported(a.cols, Nout, rows, 16, a.ld, 16, dY.ld) and
+                                 (not need_dx or lib.ipavsr_gemm_f16_supported(rows, a.cols, Nout, 16, dY.ld, 16,
+                                                                               ar.mat((l, 'W')).ld)) for a in xin))
+                    if fused:
+                        # f16x3 mode: dZ = dY act'(Y) leaves the prep kernel only as the fp16 hi/lo operand pair of the two
+                        # GEMMs below (+ the bias gradient); its scale comes from the |dY|max the producing dgrad epilogue
+                        # left behind (|act'| <= 1), else from one max pass over dY
+                        bnd = self._amax.pop((dY.ptr, dY.rows, dY.cols, dY.ld), None)
+                        if bnd is None:
+                            bt = torch.zeros(2, dtype=torch.float32, device=self.device)
+                            _lib.call('ipavsr_amax', dY.ptr, dY.ld, rows, Nout, bt.data_ptr(), st)
+                        else:
+                            bt = bnd[0]
+                        n16 = max(rows * dY.ld, 8)
+                        zhi = torch.empty(n16, dtype=torch.float16, device=self.device)
+                        zlo = torch.empty(n16, dtype=torch.float16, device=self.device)
+                        zex = torch.zeros(2, dtype=torch.float32, device=self.device)
+                        _lib.call('ipavsr_dense_bwd_prep_f16', dY.ptr, dY.ld, y.ptr, y.ld,
+                                  G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0,
+                                  bt.data_ptr(), zhi.data_ptr(), zlo.data_ptr(), dY.ld, zex.data_ptr() + 4, st)
+                        # a handle for dZ that only exists as its split: the GEMMs find it in the split cache by this key
+                        dZ = DevMat(zhi, zhi.data_ptr(), rows, Nout, dY.ld)
+                        self._split_cache[(dZ.ptr, dZ.rows, dZ.cols, dZ.ld)] = (zhi, zlo, zex, zhi)
+                    else:
+                        dZ = dY if owned else self.new(rows, Nout)
+                        amax = None
+                        if self.gemm_mode == 4:
+                            self._split_cache.pop((dZ.ptr, dZ.rows, dZ.cols, dZ.ld), None)     # dY's split (if any) is stale
+                            t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                            self._set_amax(dZ, t)
+                            amax = t.data_ptr()
+                        _lib.call('ipavsr_dense_bwd_prep', dY.ptr, dY.ld, y.ptr, y.ld, dZ.ptr, dZ.ld,
+                                  G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0,
+                                  amax, st)
                 self._proj_bwd(run, l.input_layer, xin, dZ, ar.mat((l, 'W')), G((l, 'W')))
             elif isinstance(l, L.BatchNormLayer):
                 dy = gsegs[0]
@@ -1466,7 +1507,22 @@ class Engine(object):
                 raise TypeError('unsupported layer type %s' % type(l).__name__)
             del run.grads[l]
             self._release(run, in_layers, remaining)
+            if self._ar_hi is not None and l in self._layer_lo:
+                self._ar_flush(self._layer_lo[l])
         self._join(run)
+        if self._ar_hi is not None:
+            self._ar_flush(0, final=True)
+
+    def _ar_flush(self, lo, final=False):
+        """All-reduce the finalised tail [lo, hi) of the gradient arena once it is a bucket's worth (or the walk is over)."""
+        if lo >= self._ar_hi or (not final and self._ar_hi - lo < self.ar_bucket_floats):
+            return
+        if final:
+            # the side-stream recurrences were joined: everything is ordered before this call on the main stream
+            lo = 0
+        self._ar_works.append(torch.distributed.all_reduce(self.arena.grad[lo:self._ar_hi], group=self.world[2],
+                                                           async_op=True))
+        self._ar_hi = lo
 
     def _release(self, run, ins, remaining):
         for i in ins:
@@ -1559,7 +1615,9 @@ class Engine(object):
                 continue
             self.gemm(a, dZ, dW.row_slice(k0, a.cols), a.cols, dZ.cols, a.rows, transA=1)
             if need_dx:
-                self.gemm(dZ, W.row_slice(k0, a.cols), tgt[i], a.rows, a.cols, dZ.cols, transB=1, accumulate=acc)
+                # the epilogue leaves |dX|max behind: the bound the next layer's fused backward prep scales its split with
+                self.gemm(dZ, W.row_slice(k0, a.cols), tgt[i], a.rows, a.cols, dZ.cols, transB=1, accumulate=acc,
+                          emit_split=(self.gemm_mode == 4))
             k0 += a.cols
 
     # ------------------------------------------------------------------------------------------------
@@ -1713,7 +1771,13 @@ class Engine(object):
         return np.float32(h[0] / h[1])
 
     def allreduce_grads(self):
-        if self.world is not None:
+        if self.world is None:
+            return
+        if self._ar_works or self._ar_hi == 0:
+            for w in self._ar_works:          # issued bucket by bucket during the backward walk
+                w.wait()
+            self._ar_works, self._ar_hi = [], None
+        else:
             torch.distributed.all_reduce(self.arena.grad, group=self.world[2])
 
     def read_loss(self):

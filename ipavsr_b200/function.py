@@ -179,6 +179,7 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
             return eng.loss_only(out, loss_name, y, mask, l2=l2)
         run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks)
+        eng._ar_enabled = not l2          # an L2 penalty is added to the finished gradient arena: all-reduce afterwards
         eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
                               count=float(np.asarray(mask).sum()) if (mask is not None and not hasattr(mask, 'is_cuda'))
                               else None)

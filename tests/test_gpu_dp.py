@@ -62,20 +62,27 @@ def _train(name, rank, world, steps, q=None, port=None):
     return losses, vals
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, bucket):
     torch.cuda.set_device(rank)
+    # a tiny bucket makes the overlapped all-reduce go out in many pieces during the backward walk; 0 = one all-reduce after it
+    if bucket:
+        os.environ['IPAVSR_AR_BUCKET'] = str(bucket)
+    else:
+        os.environ['IPAVSR_AR_OVERLAP'] = '0'
     _train(name, rank, world, 3, q, port)
 
 
+@pytest.mark.parametrize('bucket', [512, 0])
 @pytest.mark.parametrize('name', ['adenet_v2', 'adenet_v1'])
-def test_two_gpu_training_matches_single_gpu(name):
+def test_two_gpu_training_matches_single_gpu(name, bucket):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ref_losses, ref_vals = _train(name, 0, 1, 3)
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29900 + (abs(hash(name)) % 90)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    import zlib
+    port = 29900 + (zlib.crc32(name.encode()) % 40) * 2 + (1 if bucket else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q, bucket)) for r in range(2)]
     for p in procs:
         p.start()
     losses, vals = q.get(timeout=300)
