@@ -399,8 +399,14 @@ int ipavsr_lstm_bwd_f16_steps(const float* dout, const float* w_hid, const uint1
       if (rc) return rc;
     }
   // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step
-  int rc = gemm_simt(0, 1, N, H, 4 * H, dgates + (size_t)t_first * 4 * H, T * 4 * H, w_hid, 4 * H, w.dh_pass, H, nullptr,
-                     IPAVSR_ACT_LINEAR, 1, st);
+  int rc;
+  const size_t off_first = (size_t)t_first * 4 * H;
+  if (gemm_tc_f16_supported(N, H, 4 * H, dg_hi + off_first, T * 4 * H, whid_hi, ldw))
+    rc = gemm_tc_f16x3(0, 1, N, H, 4 * H, dg_hi + off_first, dg_lo + off_first, T * 4 * H, dg_exp, whid_hi, whid_lo, ldw,
+                       whid_exp, w.dh_pass, H, nullptr, IPAVSR_ACT_LINEAR, 1, nullptr, nullptr, nullptr, 0, st);
+  else
+    rc = gemm_simt(0, 1, N, H, 4 * H, dgates + off_first, T * 4 * H, w_hid, 4 * H, w.dh_pass, H, nullptr, IPAVSR_ACT_LINEAR,
+                   1, st);
   if (rc) return rc;
   rc = ipavsr_colsum(w.dh_pass, H, dhid_init, N, H, 1, stream);
   if (rc) return rc;

@@ -28,6 +28,11 @@ namespace ipavsr {
 
 int gemm_simt(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
               float* C, int ldc, const float* bias, int act, int accumulate, cudaStream_t st);
+int gemm_tc_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* Ahi, const uint16_t* Alo, int lda,
+                  const int32_t* expA, const uint16_t* Bhi, const uint16_t* Blo, int ldb, const int32_t* expB, float* C,
+                  int ldc, const float* bias, int act, int accumulate, float* amax, uint16_t* C16hi, uint16_t* C16lo,
+                  int c16_exp, cudaStream_t st);
+bool gemm_tc_f16_supported(int M, int N, int K, const void* A, int lda, const void* B, int ldb);
 
 namespace {
 
@@ -1011,8 +1016,15 @@ int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* w
   count_launch();
   // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step
   const int t_first = backwards ? T - 1 : 0;
-  int rc = gemm_simt(0, 1, N, H, 4 * H, dgates + (size_t)t_first * 4 * H, T * 4 * H, w_hid, 4 * H, dh_fin, H, nullptr,
-                     IPAVSR_ACT_LINEAR, 1, st);
+  int rc;
+  const size_t off_first = (size_t)t_first * 4 * H;
+  if (dg_hi != nullptr && gemm_tc_f16_supported(N, H, 4 * H, dg_hi + off_first, T * 4 * H, whid_hi, ldw))
+    // the kernel left the fp16 split of dgates behind: the rows of the first processed frame (stride T*4H) are the A operand
+    rc = gemm_tc_f16x3(0, 1, N, H, 4 * H, dg_hi + off_first, dg_lo + off_first, T * 4 * H, dg_exp, whid_hi, whid_lo, ldw,
+                       whid_exp, dh_fin, H, nullptr, IPAVSR_ACT_LINEAR, 1, nullptr, nullptr, nullptr, 0, st);
+  else
+    rc = gemm_simt(0, 1, N, H, 4 * H, dgates + off_first, T * 4 * H, w_hid, 4 * H, dh_fin, H, nullptr, IPAVSR_ACT_LINEAR, 1,
+                   st);
   if (rc) return rc;
   rc = ipavsr_colsum(dh_fin, H, dhid_init, N, H, 1, stream);
   if (rc) return rc;

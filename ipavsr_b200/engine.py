@@ -335,6 +335,24 @@ class _Profiler(object):
         return out
 
 
+class _Nvtx(object):
+    """NVTX ranges around the phases of a step and around every layer (IPAVSR_NVTX=1): Nsight Systems / Compute group the
+    kernels of the forward walk, the backward walk, the gradient all-reduce and the update by the reference layer names
+    (`fc1_s1`, `lstm_s2`, `f_lstm_agg` ...).  Off by default: a push/pop pair per layer costs host time."""
+    on = os.environ.get('IPAVSR_NVTX', '0') == '1'
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_pop()
+
+
 class _Run(object):
     """Per-call state: values, saved tensors for backward, gradients."""
 
@@ -466,6 +484,8 @@ class Engine(object):
         self._copy_stream = None
         self._prefetched = []
         self._c14 = None
+        self._zpool, self._zpos = None, 0
+        self._opool, self._opos = None, 0
         # fp16 hi/lo of sigmoid/tanh outputs written by the GEMM epilogue itself (static scale 2^14, coalesced through the
         # epilogue's staging tile): saves the separate split pass over those activations (IPAVSR_EPILOGUE_SPLIT=0 disables)
         self.epilogue_split = os.environ.get('IPAVSR_EPILOGUE_SPLIT', '1') == '1'
@@ -557,6 +577,27 @@ class Engine(object):
             self._split_cache[key] = hit
         return hit[0], hit[1]
 
+    def _zeros2(self):
+        """Two zeroed floats ([|x|max, scale exponent] of an operand, a bound ...) carved out of one pre-zeroed pool per
+        step: one fill kernel instead of one per request (66 of the 220 launches of a step were these fills)."""
+        if self._zpool is None or self._zpos + 8 > self._zpool.numel():
+            self._zpool = torch.zeros(2048, dtype=torch.float32, device=self.device)
+            self._zpos = 0
+        t = self._zpool[self._zpos: self._zpos + 2]
+        self._zpos += 8                       # 32-byte slots
+        return t
+
+    def _ones2(self):
+        """[1.0, 0]: the starting value of a bound max(1, ...) — from a pool filled once per step."""
+        if self._opool is None or self._opos + 8 > self._opool.numel():
+            self._opool = torch.zeros(32, 8, dtype=torch.float32, device=self.device)
+            self._opool[:, 0] = 1.0
+            self._opool = self._opool.view(-1)
+            self._opos = 0
+        t = self._opool[self._opos: self._opos + 2]
+        self._opos += 8
+        return t
+
     def _set_amax(self, m, t):
         """Registers the device max|m| produced alongside `m`.  The entry holds m's storage: while it exists the
         allocator cannot hand the same address to another buffer that would then read a stale 'ready' scale."""
@@ -565,7 +606,7 @@ class Engine(object):
     def _const14(self):
         """[amax = 1.0, exponent = 14] for tensors bounded by 1 (sigmoid / tanh activations, LSTM hidden states)."""
         if self._c14 is None:
-            t = torch.zeros(2, dtype=torch.float32, device=self.device)
+            t = self._zeros2()
             t[0] = 1.0
             t[1:2].view(torch.int32)[0] = 14
             self._c14 = t
@@ -631,7 +672,7 @@ class Engine(object):
                     else:
                         # the epilogue leaves max|C| behind, so the split of C (first use as an operand) needs no
                         # reduction pass
-                        t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                        t = self._zeros2()
                         self._set_amax(Cm, t)
                         amax = t.data_ptr()
                 _lib.call('ipavsr_gemm_f16x3', transA, transB, M, N, K, ah, al, A.ld, ea, bh, bl, B.ld, eb,
@@ -1015,6 +1056,7 @@ class Engine(object):
                 break
         N, T = int(first.shape[0]), int(first.shape[1])
         run = _Run(N, T)
+        self._zpool = self._opool = None    # small zeroed / one-initialised scratch: fresh pools per step
         self.arena.sync_from_peers()
         pre = self._take_prefetched(inputs)
         if pre is not None:
@@ -1032,6 +1074,17 @@ class Engine(object):
         run.deterministic = deterministic
         ar = self.arena
         for l in self.layers:
+            if _Nvtx.on:
+                torch.cuda.nvtx.range_push('fwd %s' % (l.name or type(l).__name__))
+            self._forward_layer(run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn)
+            if _Nvtx.on:
+                torch.cuda.nvtx.range_pop()
+        return self._forward_finish(run)
+
+    def _forward_layer(self, run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn):
+        lib, st, ar = self.lib, self.stream, self.arena
+        N, T = run.N, run.T
+        if True:
             for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
                 if i is not None and i in run.pending and not (isinstance(l, L.LSTMLayer) and i in self.mask_layers):
                     self._wait(run, i)
@@ -1057,7 +1110,7 @@ class Engine(object):
                 elif len(segs) == 1 and segs[0].chunks and self.gemm_mode == 4:
                     # the input is still arriving: one product per row chunk, each split with its own scale
                     x = segs[0]
-                    amax_t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                    amax_t = self._zeros2()
                     for (r0, n, ev) in x.chunks:
                         torch.cuda.current_stream(self.device).wait_event(ev)
                         self.gemm(x.row_slice(r0, n), W, out.row_slice(r0, n), n, out.cols, x.cols, 0, 0, b,
@@ -1148,8 +1201,7 @@ class Engine(object):
                     cl, coff = self.cat_of[l]
                     if cl not in run.cat:
                         total = self.cat_plan[cl][1]
-                        bound = torch.zeros(2, dtype=torch.float32, device=self.device)
-                        bound[0] = 1.0
+                        bound = self._ones2()
                         run.cat[cl] = (self.new(N * T, total, zero=(_ld8(total) != total)), bound)
                     cat, cat_bound = run.cat[cl]
                     out = DevMat(cat.t, cat.ptr + 4 * coff, N * T, H, cat.ld)
@@ -1213,8 +1265,7 @@ class Engine(object):
                 if self.gemm_mode == 4:
                     # h = o * tanh(c) lies in (-1, 1); padded / first steps carry hid_init: |out|, |hprev| <= max(1, |hid_init|)
                     # is known without a pass over the (N*T, H) tensors
-                    bound = torch.zeros(2, dtype=torch.float32, device=self.device)
-                    bound[0] = 1.0
+                    bound = self._ones2()
                     _lib.call('ipavsr_amax', ar.mat((l, 'hid_init')).ptr, H, 1, H, bound.data_ptr(), st)
                     if cat_bound is not None:
                         # the materialised concat is bounded by the largest of its LSTMs' bounds (atomic max, same stream)
@@ -1222,7 +1273,7 @@ class Engine(object):
                     else:
                         self._set_amax(out, bound)
                     if hprev is not None:
-                        self._set_amax(hprev, bound.clone())
+                        self._set_amax(hprev, bound)       # same bound, same scale exponent: the two splits share the pair
             elif isinstance(l, (L.ElemwiseSumLayer, L.AdaptiveElemwiseSumLayer)):
                 ins = [self._single(run.vals[i]) for i in l.input_layers]
                 rows, F = ins[0].rows, ins[0].cols
@@ -1250,6 +1301,10 @@ class Engine(object):
                 run.vals[l] = [out]
             else:
                 raise TypeError('unsupported layer type %s' % type(l).__name__)
+
+    def _forward_finish(self, run):
+        plan, st = run.plan, self.stream
+        N, T = run.N, run.T
         self._join(run)
         outv = run.vals[self.out]
         run.out_sorted = outv
@@ -1348,6 +1403,8 @@ class Engine(object):
             if l not in run.grads or isinstance(l, L.InputLayer):
                 self._release(run, in_layers, remaining)
                 continue
+            if _Nvtx.on:
+                torch.cuda.nvtx.mark('bwd %s' % (l.name or type(l).__name__))
             gsegs, _ = run.grads[l]
             if isinstance(l, L.ReshapeLayer):
                 self._pass_grad(run, l.input_layer, gsegs)
@@ -1388,14 +1445,14 @@ class Engine(object):
                         # left behind (|act'| <= 1), else from one max pass over dY
                         bnd = self._amax.pop((dY.ptr, dY.rows, dY.cols, dY.ld), None)
                         if bnd is None:
-                            bt = torch.zeros(2, dtype=torch.float32, device=self.device)
+                            bt = self._zeros2()
                             _lib.call('ipavsr_amax', dY.ptr, dY.ld, rows, Nout, bt.data_ptr(), st)
                         else:
                             bt = bnd[0]
                         n16 = max(rows * dY.ld, 8)
                         zhi = torch.empty(n16, dtype=torch.float16, device=self.device)
                         zlo = torch.empty(n16, dtype=torch.float16, device=self.device)
-                        zex = torch.zeros(2, dtype=torch.float32, device=self.device)
+                        zex = self._zeros2()
                         _lib.call('ipavsr_dense_bwd_prep_f16', dY.ptr, dY.ld, y.ptr, y.ld,
                                   G((l, 'b')).ptr if l.b is not None else None, rows, Nout, ACT[l.nonlinearity.name], 0,
                                   bt.data_ptr(), zhi.data_ptr(), zlo.data_ptr(), dY.ld, zex.data_ptr() + 4, st)
@@ -1407,7 +1464,7 @@ class Engine(object):
                         amax = None
                         if self.gemm_mode == 4:
                             self._split_cache.pop((dZ.ptr, dZ.rows, dZ.cols, dZ.ld), None)     # dY's split (if any) is stale
-                            t = torch.zeros(2, dtype=torch.float32, device=self.device)
+                            t = self._zeros2()
                             self._set_amax(dZ, t)
                             amax = t.data_ptr()
                         _lib.call('ipavsr_dense_bwd_prep', dY.ptr, dY.ld, y.ptr, y.ld, dZ.ptr, dZ.ld,
@@ -1560,7 +1617,7 @@ class Engine(object):
             n = max(dG.rows * dG.ld, 8)
             ghi = torch.empty(n, dtype=torch.float16, device=self.device)
             glo = torch.empty(n, dtype=torch.float16, device=self.device)
-            gex = torch.zeros(2, dtype=torch.float32, device=self.device)
+            gex = self._zeros2()
             self._split_cache[(dG.ptr, dG.rows, dG.cols, dG.ld)] = (ghi, glo, gex, dG.t)
             self._split_by_storage.setdefault(id(dG.t), []).append((dG.ptr, dG.rows, dG.cols, dG.ld))
             sbytes = int(lib.ipavsr_lstm_steps_workspace_bytes(N, T, H))
@@ -1580,7 +1637,7 @@ class Engine(object):
                 n = max(dG.rows * dG.ld, 8)
                 ghi = torch.empty(n, dtype=torch.float16, device=self.device)
                 glo = torch.empty(n, dtype=torch.float16, device=self.device)
-                gex = torch.zeros(2, dtype=torch.float32, device=self.device)
+                gex = self._zeros2()
                 self._split_cache[(dG.ptr, dG.rows, dG.cols, dG.ld)] = (ghi, glo, gex, dG.t)
                 self._split_by_storage.setdefault(id(dG.t), []).append((dG.ptr, dG.rows, dG.cols, dG.ld))
             _lib.call('ipavsr_lstm_bwd_f16', dout.ptr, whid.ptr, wh, wl, we, whid.ld, peep, ar.mat((l, 'cell_init')).ptr,

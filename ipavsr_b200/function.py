@@ -14,7 +14,7 @@ callable with the same positional arguments that runs the B200 engine.
 import numpy as np
 
 from . import layers as L
-from .engine import get_engine
+from .engine import get_engine, _Nvtx
 
 
 class _TensorNamespace(object):
@@ -178,18 +178,22 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         if not train:
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
             return eng.loss_only(out, loss_name, y, mask, l2=l2)
-        run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks)
+        with _Nvtx('forward'):
+            run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks)
         eng._ar_enabled = not l2          # an L2 penalty is added to the finished gradient arena: all-reduce afterwards
-        eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
-                              count=float(np.asarray(mask).sum()) if (mask is not None and not hasattr(mask, 'is_cuda'))
-                              else None)
-        if l2:
-            eng.l2_penalty(l2)
-        eng.allreduce_grads()
+        with _Nvtx('loss + backward'):
+            eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
+                                  count=float(np.asarray(mask).sum()) if (mask is not None and not hasattr(mask, 'is_cuda'))
+                                  else None)
+            if l2:
+                eng.l2_penalty(l2)
+        with _Nvtx('gradient all-reduce'):
+            eng.allreduce_grads()
         u = updates
         lr = _lr_value(u.lr) if u.lr is not None else 0.0
         lr_map = u.lr_map if subset is None else {p: lr for p in subset}
-        eng.optim_step(u.kind, lr, params=u.params, lr_map=lr_map, **u.hp)
+        with _Nvtx('update (%s)' % u.kind):
+            eng.optim_step(u.kind, lr, params=u.params, lr_map=lr_map, **u.hp)
         return eng.read_loss()
 
     def prefetch(*args, **kw):

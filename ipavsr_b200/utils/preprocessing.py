@@ -1,6 +1,8 @@
 """`utils/preprocessing.py` of the reference, hot-path subset (SURVEY §8a rows a10–a14), executed by the sm_100a
-kernels of csrc/preprocess.cu.  Same names, argument meaning and return values; arrays go host -> device -> host per
-call (use `ipavsr_b200.utils.device_pre` objects to keep a dataset resident in HBM instead).
+kernels of csrc/preprocess.cu.  Same names, argument meaning and return values.  A NumPy array goes host -> device -> host
+per call and comes back as a NumPy array (the reference's contract); a CUDA `torch` tensor stays in HBM — the result is a
+CUDA tensor and nothing is copied, so a dataset can be normalised / differenced / projected once, kept resident
+(`utils.datagen.DeviceDataset`) and fed to the compiled functions without ever crossing the host link.
 
 No CPU fallback: these raise without a CUDA device.
 """
@@ -16,10 +18,22 @@ def _st():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _is_dev(a):
+    return isinstance(a, torch.Tensor) and a.is_cuda
+
+
 def _dev(a, dtype=np.float32):
     if not torch.cuda.is_available():
         raise RuntimeError('ipavsr_b200.utils.preprocessing needs a CUDA device (there is no CPU path)')
+    if isinstance(a, torch.Tensor):
+        t = a.to(device='cuda', dtype=torch.from_numpy(np.zeros(0, dtype)).dtype)
+        return t.contiguous()
     return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+def _out(t, like):
+    """Result in the form of the input: CUDA tensor for a CUDA tensor (no copy), NumPy array otherwise."""
+    return t if _is_dev(like) else t.cpu().numpy()
 
 
 def _offsets(seqlens):
@@ -35,6 +49,11 @@ def normalize_input(input, centralize=True, quantize=False):
     frames, D = x.shape
     y = torch.empty_like(x)
     _lib.call('ipavsr_norm_samplewise', x.data_ptr(), D, y.data_ptr(), D, frames, D, _st())
+    if _is_dev(input):
+        if input.dtype == torch.float32 and input.is_contiguous():
+            input.copy_(y)                   # in place, like the reference
+            return input
+        return y
     out = y.cpu().numpy()
     if isinstance(input, np.ndarray) and input.dtype == np.float32:
         input[...] = out                     # the reference normalises in place and returns the same array
@@ -54,7 +73,7 @@ def featurewise_normalize_sequence(input):
     y = torch.empty_like(x)
     _lib.call('ipavsr_norm_featurewise_apply', x.data_ptr(), F, mean.data_ptr(), std.data_ptr(), y.data_ptr(), F,
               frames, F, _st())
-    return y.cpu().numpy(), mean.cpu().numpy(), std.cpu().numpy()
+    return _out(y, input), _out(mean, input), _out(std, input)
 
 
 def featurewise_apply(input, mean, std):
@@ -65,7 +84,7 @@ def featurewise_apply(input, mean, std):
     m, s = _dev(mean), _dev(std)
     _lib.call('ipavsr_norm_featurewise_apply', x.data_ptr(), F, m.data_ptr(), s.data_ptr(), y.data_ptr(), F, frames, F,
               _st())
-    return y.cpu().numpy()
+    return _out(y, input)
 
 
 def _per_utterance(name, input, seqlens):
@@ -80,7 +99,7 @@ def _per_utterance(name, input, seqlens):
     for u0 in range(0, U, 65535):
         n = min(65535, U - u0)
         _lib.call(name, x.data_ptr(), D, y.data_ptr(), D, d_offs.data_ptr() + 8 * u0, n, D, _st())
-    return y.cpu().numpy()
+    return _out(y, input)
 
 
 def sequencewise_mean_image_subtraction(input, seqlens, axis=0):
@@ -110,7 +129,7 @@ def concat_first_second_deltas(X, vidlenvec, w=9):
         n = min(65535, U - u0)
         _lib.call('ipavsr_deltas_fir', x.data_ptr(), F, y.data_ptr(), 3 * F, d_offs.data_ptr() + 8 * u0, n, F, int(w),
                   int(lens.max()), _st())
-    return y.cpu().numpy()
+    return _out(y, X)
 
 
 def deltas(x, w=9):
@@ -177,7 +196,7 @@ def compute_dct_features(X, image_shape, no_coeff=30, method='zigzag'):
         if int(image_shape[0]) * int(image_shape[1]) != D:
             raise ValueError('cannot reshape array of size %d into shape %r' % (D, tuple(image_shape)))
         cols = zigzag_order(*image_shape)[1:no_coeff + 1]
-        return _dct_project(x, cols).cpu().numpy()
+        return _out(_dct_project(x, cols), X)
     ac = _dct_project(x, np.arange(1, D))                     # X_dct[:, 1:]
     F = D - 1
     if method == 'energy':
@@ -194,7 +213,7 @@ def compute_dct_features(X, image_shape, no_coeff=30, method='zigzag'):
     K = len(idxs)
     out = torch.empty(frames, K, dtype=torch.float32, device='cuda')
     _lib.call('ipavsr_gather_cols', ac.data_ptr(), F, d_idx.data_ptr(), out.data_ptr(), K, frames, K, _st())
-    return out.cpu().numpy()
+    return _out(out, X)
 
 
 def reorder_data(X, shape, orig_order='f', desired_order='c'):
@@ -203,13 +222,13 @@ def reorder_data(X, shape, orig_order='f', desired_order='c'):
     orig_order, desired_order = orig_order.lower(), desired_order.lower()
     if orig_order not in 'fc' or desired_order not in 'fc':
         raise ValueError("order must be 'f' or 'c'")
-    x = _dev(np.asarray(X).reshape(-1, d1 * d2))
+    x = _dev(X.reshape(-1, d1 * d2) if _is_dev(X) else np.asarray(X).reshape(-1, d1 * d2))
     if orig_order == desired_order:
-        return x.cpu().numpy()
+        return _out(x, X)
     y = torch.empty_like(x)
     _lib.call('ipavsr_reorder', x.data_ptr(), d1 * d2, y.data_ptr(), d1 * d2, x.shape[0], d1, d2,
               1 if desired_order == 'c' else 0, _st())
-    return y.cpu().numpy()
+    return _out(y, X)
 
 
 def _align_plan(lens_in, lens_out, fill_rel):
