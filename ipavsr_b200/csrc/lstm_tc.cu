@@ -12,10 +12,14 @@
 //   * its W_hid^T slice (fp16 hi and lo, 2 x 64 KB at K = 256) is loaded ONCE by TMA, straight from the engine's fp16
 //     split of the parameter arena (MN-major SWIZZLE_128B operand: no transposed copy), and stays in shared memory;
 //   * h_t (fp16 hi/lo, scale 2^eH with eH from max(1, |hid_init|)) lives in a double-buffered K-major SWIZZLE_64B
-//     operand tile; after the cell update every CTA converts its 32 units x 32 utterances of h_{t+1} into that layout
-//     in a staging buffer and pushes it into the next-step tile of all CS CTAs with cp.async.bulk
-//     (shared::cta -> shared::cluster), completing on the destination's mbarrier (complete_tx) — the MMA thread of each
-//     CTA simply waits for CS x 4 KB to land: there is no cluster barrier in the time loop;
+//     operand tile; after the cell update every CTA converts its 32 units x 32 utterances of h_{t+1} into that layout,
+//     writes it straight into its own slot of its next-step tile and into a staging buffer that it pushes into the
+//     next-step tile of the CS-1 OTHER CTAs with cp.async.bulk (shared::cta -> shared::cluster), completing on the
+//     destination's mbarrier (complete_tx) — the MMA thread of each CTA waits for (CS-1) x 4 KB to land plus one arrival of
+//     its own epilogue: there is no cluster barrier in the time loop.  (The bulk copy is specified for REMOTE destinations
+//     only: compute-sanitizer flagged the earlier self-push, profiles/r02_sanitizer_summary.md.)
+//   * frames at which every utterance of the tile is masked are skipped (no MMAs, no exchange): with the engine's
+//     length-sorted batches a tile runs max(len) steps instead of T;
 //   * 128 epilogue threads own one TMEM lane each (gate column 4u+g): tcgen05.ld, add the hoisted input projection
 //     xw[t] (coalesced: a warp reads 32 consecutive gate columns of one frame), a 4x4 shuffle transpose brings the four
 //     gates of a (unit, utterance) cell into one thread, which then owns 8 cells.
@@ -242,8 +246,10 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    q_mbar_init(&hbar[0], 1);
-    q_mbar_init(&hbar[1], 1);
+    // two arrivals per phase: the control thread's expect_tx (bytes pushed by the OTHER CTAs) and the epilogue's arrival
+    // after it has written this CTA's own chunk of h straight into the tile
+    q_mbar_init(&hbar[0], 2);
+    q_mbar_init(&hbar[1], 2);
     q_mbar_init(&accbar, 1);
     q_mbar_init(&wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -315,7 +321,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         const int b = k & 1;               // k counts the active steps: buffers and barrier phases alternate on it
         const long long c0 = q_clock();
         if (k > 0) {
-          q_mbar_expect_tx(&hbar[b], (uint32_t)CS * 4096u);
+          q_mbar_expect_tx(&hbar[b], (uint32_t)(CS - 1) * 4096u);
           q_mbar_wait(&hbar[b], hphase[b]);
           hphase[b] ^= 1;
         }
@@ -463,6 +469,9 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         a[4 * i] = x0; a[4 * i + 1] = x1; a[4 * i + 2] = x2; a[4 * i + 3] = x3;
       }
       uint8_t* stg = sStage + (size_t)(k & 1) * 4096;
+      // this CTA's own slot of the next-step operand tile (buffer (k+1)&1 was last read by the MMAs of step k-1, which
+      // completed before the accumulator of step k did): written directly, the other CTAs get the staged copy pushed
+      uint8_t* own = sH + (size_t)((k + 1) & 1) * 2 * HBYTES + (size_t)rank * 2048;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool mk = (mbits[i] >> t) & 1ull;
@@ -484,19 +493,24 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         const uint32_t off = q_sw64(j0 + 4 * i + g, ul);
         *reinterpret_cast<__half*>(stg + off) = hi;
         *reinterpret_cast<__half*>(stg + 2048 + off) = lo;
+        *reinterpret_cast<__half*>(own + off) = hi;
+        *reinterpret_cast<__half*>(own + HBYTES + off) = lo;
       }
       const long long k3 = q_clock();
       e_math += k3 - k2;
       if (s_next < T) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        // push my chunk of h_{t+1} into the next-step operand tile of every CTA of the cluster (my own included)
-        if (tid < CS) {
-          const int nb = (k + 1) & 1;
+        // push my chunk of h_{t+1} into the next-step operand tile of every OTHER CTA of the cluster (bulk shared::cta ->
+        // shared::cluster copies completing on the destination's barrier); my own tile already holds it: one arrival
+        const int nb = (k + 1) & 1;
+        if (tid < CS && tid != rank) {
           const uint32_t dst_hi = q_smem(sH + (size_t)nb * 2 * HBYTES + (size_t)rank * 2048);
           const uint32_t bar = q_mapa(q_smem(&hbar[nb]), (uint32_t)tid);
           q_bulk_s2s(q_mapa(dst_hi, (uint32_t)tid), q_smem(stg), 2048, bar);
           q_bulk_s2s(q_mapa(dst_hi + HBYTES, (uint32_t)tid), q_smem(stg + 2048), 2048, bar);
+        } else if (tid == rank) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(q_smem(&hbar[nb])) : "memory");
         }
       }
       e_push += q_clock() - k3;
