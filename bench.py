@@ -537,7 +537,9 @@ def main():
         i = jt[0]
         jt[0] += 1
         if not args.no_prefetch:
-            train.prefetch(*cache[(i + 1) % NB])     # the next step's upload overlaps this step's compute
+            # the next step's upload is staged by this call once its own kernels are enqueued (before it reads the loss
+            # back): the upload overlaps this step's compute and the staging work hides behind it
+            train.prefetch(*cache[(i + 1) % NB], defer=True)
         return train(*cache[i % NB])
     ms_e2e, _ = timed(step_e2e, args.steps, 3)
     eng._prefetched = []
@@ -563,7 +565,7 @@ def main():
         i = kt[0]
         kt[0] += 1
         nx = hp[(i + 1) % 2]
-        train.prefetch(nx[0][0], nx[0][1], nx[0][2], nx[2], nx[1], THETA)
+        train.prefetch(nx[0][0], nx[0][1], nx[0][2], nx[2], nx[1], THETA, defer=True)
         cx = hp[i % 2]
         return train(cx[0][0], cx[0][1], cx[0][2], cx[2], cx[1], THETA)
     ms_e2e_p, _ = timed(step_e2e_padded, max(4, args.steps // 2), 2)

@@ -17,6 +17,7 @@
 //       - backward of the unpack: the gradient of the constant row is the sum of the gradients of all padding rows.
 //
 // HBM-bound (or PCIe-bound) copies: one warp per row, consecutive rows on consecutive warps.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ipavsr {
@@ -88,13 +89,24 @@ extern "C" int ipavsr_gather_rows(const void* src, int64_t src_pitch_bytes, void
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   long long blocks = (rows + 7) / 8;
   // A device source is an HBM-bound copy: fill the machine.  A pinned-host source is PCIe-bound (~50 GB/s needs only a
-  // few hundred KB in flight) and runs on a copy stream NEXT to the compute kernels: one CTA per SM leaves the thread
-  // slots of every SM to them (8 CTAs x 256 threads would occupy all 2048 and serialise the step behind the upload).
+  // few hundred KB in flight) and runs on a copy stream NEXT to the compute kernels.  Measured (tools/overlap_probe.py):
+  // an SM that holds one of these CTAs does not accept a GEMM / LSTM CTA launched AFTER it (a 148-CTA upload launched
+  // first delays the GEMM stream by its whole 1.4 ms; launched after the GEMMs it costs them 0.35 ms), and 16-32 CTAs
+  // already saturate the link — so the grid is small (IPAVSR_HOST_GATHER_CTAS, default 32) and the engine issues the
+  // upload of the NEXT step after the current step's kernels (function(...).prefetch(defer=True)).
   long long cap = (long long)sm_count() * 8;
   if (src != nullptr) {
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) cap = sm_count();
-    else (void)cudaGetLastError();
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+      static int host_ctas = -1;
+      if (host_ctas < 0) {
+        const char* e = getenv("IPAVSR_HOST_GATHER_CTAS");
+        host_ctas = (e && atoi(e) > 0) ? atoi(e) : 32;
+      }
+      cap = host_ctas;
+    } else {
+      (void)cudaGetLastError();
+    }
   }
   if (blocks > cap) blocks = cap;
   const uintptr_t all = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) |
@@ -103,12 +115,13 @@ extern "C" int ipavsr_gather_rows(const void* src, int64_t src_pitch_bytes, void
   const uint8_t* s = static_cast<const uint8_t*>(src);
   uint8_t* d = static_cast<uint8_t*>(dst);
   const uint8_t* f = static_cast<const uint8_t*>(fill_row);
+  const size_t dyn = 0;
   if ((all & 15) == 0)
-    gather_rows_kernel<16><<<(int)blocks, 256, 0, st>>>(s, src_pitch_bytes, d, dst_pitch_bytes, row_bytes, idx, f, rows);
+    gather_rows_kernel<16><<<(int)blocks, 256, dyn, st>>>(s, src_pitch_bytes, d, dst_pitch_bytes, row_bytes, idx, f, rows);
   else if ((all & 3) == 0)
-    gather_rows_kernel<4><<<(int)blocks, 256, 0, st>>>(s, src_pitch_bytes, d, dst_pitch_bytes, row_bytes, idx, f, rows);
+    gather_rows_kernel<4><<<(int)blocks, 256, dyn, st>>>(s, src_pitch_bytes, d, dst_pitch_bytes, row_bytes, idx, f, rows);
   else
-    gather_rows_kernel<1><<<(int)blocks, 256, 0, st>>>(s, src_pitch_bytes, d, dst_pitch_bytes, row_bytes, idx, f, rows);
+    gather_rows_kernel<1><<<(int)blocks, 256, dyn, st>>>(s, src_pitch_bytes, d, dst_pitch_bytes, row_bytes, idx, f, rows);
   IPAVSR_LAUNCH_CHECK();
   return IPAVSR_OK;
 }

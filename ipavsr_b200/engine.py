@@ -286,6 +286,7 @@ class _PackPlan(object):
         self.tables = [('pack', pack), ('valid', valid), ('unpack', unpack), ('perm', perm), ('unperm', unperm),
                        ('order', order.astype(np.int32)), ('inv', inv), ('mask', mask4.view(np.int32))]
         self.dev = None
+        self.ready = None            # event: the tables are on the device
 
     def upload(self, device, pinned):
         """One host->device copy of all tables (through the pinned staging tensor `pinned`, int32, large enough)."""
@@ -765,25 +766,59 @@ class Engine(object):
                 return plan
         plan = _PackPlan(lens, T)
         need = sum(len(a) for _, a in plan.tables)
-        # pinned staging ring: a buffer is reused only after the copy that last read it has completed
+        slot = self._pin_ring(need)
+        with torch.cuda.device(self.device):
+            plan.upload(self.device, slot[0])
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        slot[1] = ev
+        plan.ready = ev
+        self._plans.insert(0, (key, plan))
+        del self._plans[8:]
+        return plan
+
+    def _pin_ring(self, need):
+        """A pinned int32 staging tensor of at least `need` elements from a ring of 4: [tensor, event of the copy that last
+        read it].  A slot is reused only after that copy has completed, so asynchronous H2D copies never see it change."""
         if len(self._plan_pins) < 4:
             self._plan_pins.insert(0, [torch.empty(max(need, 1 << 16), dtype=torch.int32).pin_memory(), None])
         else:
             self._plan_pins.insert(0, self._plan_pins.pop())
             if self._plan_pins[0][1] is not None:
                 self._plan_pins[0][1].synchronize()
-            if self._plan_pins[0][0].numel() < need:
-                self._plan_pins[0][0] = torch.empty(need, dtype=torch.int32).pin_memory()
         if self._plan_pins[0][0].numel() < need:
             self._plan_pins[0][0] = torch.empty(need, dtype=torch.int32).pin_memory()
-        with torch.cuda.device(self.device):
-            plan.upload(self.device, self._plan_pins[0][0])
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
-        self._plan_pins[0][1] = ev
-        self._plans.insert(0, (key, plan))
-        del self._plans[8:]
-        return plan
+        return self._plan_pins[0]
+
+    def _stage_targets(self, run, y):
+        """Targets of a training / cost call -> device int32 BEFORE the forward kernels are enqueued, in the run's utterance
+        order, through pinned staging.  (A pageable host->device copy issued after the forward pass blocks the host until
+        the forward has finished on the device, and the backward is then enqueued onto an idle GPU: 1.4 ms per step.)"""
+        plan = run.plan
+        if y is None or isinstance(y, DevMat):
+            return
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            if plan is None:
+                run.targets_dev = y.to(torch.int32).contiguous()
+            else:
+                ys = y.to(torch.int32).contiguous().view(plan.N, -1)
+                yd = torch.empty_like(ys)
+                _lib.call('ipavsr_gather_rows', ys.data_ptr(), 4 * ys.shape[1], yd.data_ptr(), 4 * ys.shape[1],
+                          4 * ys.shape[1], plan.order.data_ptr(), None, plan.N, self.stream)
+                run.targets_dev = yd.view(y.shape)
+            return
+        yh = y.numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
+        if yh.dtype.kind not in 'iub':
+            return                                   # regression targets (float): uploaded by the loss
+        if plan is not None:
+            yh = yh[plan.order_host]
+        yh = np.ascontiguousarray(yh, dtype=np.int32)
+        slot = self._pin_ring(yh.size)
+        slot[0][:yh.size].numpy()[:] = yh.ravel()
+        run.targets_dev = slot[0][:yh.size].to(self.device, non_blocking=True).view(yh.shape)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        slot[1] = ev
 
     def _gather(self, src_ptr, src_pitch, rows_out, cols, idx, keep=None, stream=None):
         """DevMat (rows_out x cols) = rows of a float32 matrix at `src_ptr` (row pitch src_pitch floats; device memory or
@@ -911,7 +946,12 @@ class Engine(object):
             self._copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
         cs = self._copy_stream
-        cs.wait_stream(main)            # buffers recycled by the allocator may still be read by earlier kernels
+        # The staging buffers are allocated with the copy stream current: they come from that stream's pool of the caching
+        # allocator, which hands a block out again only after every stream it was recorded on has passed its last use —
+        # the copies need not wait for the compute stream (they did, which kept an upload issued behind a step's kernels
+        # from overlapping them).  What the copies do read from the compute stream is the plan's index tables.
+        if plan is not None and plan.ready is not None:
+            cs.wait_event(plan.ready)
         staged = {}
         # the mask first (tiny, needed by every LSTM), then the streams in graph order
         order = [l for l in host if l in self.mask_layers] + [l for l in host if l not in self.mask_layers]
@@ -1046,7 +1086,7 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------------
-    def forward(self, inputs, window, deterministic=True, train=False, dropout_masks=None, update_bn=True):
+    def forward(self, inputs, window, deterministic=True, train=False, dropout_masks=None, update_bn=True, targets=None):
         """inputs: {InputLayer: array}.  Returns (_Run, output Val).  `train` keeps what backward needs."""
         lib, st = self.lib, self.stream
         first = None
@@ -1065,6 +1105,8 @@ class Engine(object):
             plan = self._get_plan(inputs)
             staged = self._stage_inputs(inputs, plan=plan)
         run.plan = plan
+        run.targets_dev = None
+        self._stage_targets(run, targets)
         self._split_cache = {}
         self._split_by_storage = {}
         self._amax = {}
@@ -1693,16 +1735,10 @@ class Engine(object):
         dlogits = self.new(p.rows, p.cols)
         if loss == 'squared_error':
             yd = None
-        elif plan is None:
-            yd = self._upload(y, 'int')
-        elif isinstance(y, torch.Tensor) and y.is_cuda:
-            ys = y.to(torch.int32).contiguous().view(plan.N, -1)
-            yd = torch.empty_like(ys)
-            _lib.call('ipavsr_gather_rows', ys.data_ptr(), 4 * ys.shape[1], yd.data_ptr(), 4 * ys.shape[1],
-                      4 * ys.shape[1], plan.order.data_ptr(), None, plan.N, st)
         else:
-            yh = y.numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
-            yd = self._upload(yh[plan.order_host], 'int')
+            if run.targets_dev is None:
+                self._stage_targets(run, y)
+            yd = run.targets_dev
         count_dev = None
         if loss == 'temporal_softmax':
             if plan is not None:

@@ -170,6 +170,7 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
                 # the result stays in HBM as a torch tensor (on-device evaluation, utils/evaluate.py)
                 res = eng.read_device(out)
                 return res.reshape(run.N, run.T, -1) if len(lay.output_shape) == 3 else res
+            _run_deferred()
             res = eng.read(out)
             if len(lay.output_shape) == 3:
                 res = res.reshape(run.N, run.T, -1)
@@ -179,7 +180,7 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
             return eng.loss_only(out, loss_name, y, mask, l2=l2)
         with _Nvtx('forward'):
-            run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks)
+            run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks, targets=y)
         eng._ar_enabled = not l2          # an L2 penalty is added to the finished gradient arena: all-reduce afterwards
         with _Nvtx('loss + backward'):
             eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
@@ -194,21 +195,38 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         lr_map = u.lr_map if subset is None else {p: lr for p in subset}
         with _Nvtx('update (%s)' % u.kind):
             eng.optim_step(u.kind, lr, params=u.params, lr_map=lr_map, **u.hp)
+        _run_deferred()
         return eng.read_loss()
 
+    pending = []
+
+    def _run_deferred():
+        while pending:
+            eng.prefetch(pending.pop(0))
+
     def prefetch(*args, **kw):
-        """Start the host->device copy of the NEXT call's inputs (same positional arguments as the call itself) on the
-        engine's copy stream and return at once: the copy overlaps whatever the device is doing, and the matching call
-        picks the staged buffers up instead of copying again.  A double-buffered loader in two lines:
+        """Stage the host inputs of a LATER call (same positional arguments as the call itself) on the engine's copy stream:
+        the copy overlaps whatever the device is doing, and the matching call picks the staged buffers up instead of
+        copying again.  `defer=True` postpones the staging to the next call of this function, which performs it after it
+        has enqueued its own kernels and before it blocks on its result — the recommended double-buffered loop:
 
             train.prefetch(*batch[0])
             for i in range(n):
-                if i + 1 < n: train.prefetch(*batch[i + 1])
+                if i + 1 < n: train.prefetch(*batch[i + 1], defer=True)
                 cost = train(*batch[i])
+
+        The host buffers must stay unchanged until the matching call has returned (pinned memory is read asynchronously).
         """
         if len(args) != len(slots):
             raise TypeError('expected %d arguments, got %d' % (len(slots), len(args)))
-        eng.prefetch({layer: a for (kind, layer), a in zip(slots, args) if kind == 'input'})
+        feed = {layer: a for (kind, layer), a in zip(slots, args) if kind == 'input'}
+        if kw.get('defer'):
+            # staged by the NEXT call of this function, after it has enqueued its own kernels and before it waits for its
+            # result: the host work of staging hides behind the device's compute, and an upload issued behind the
+            # compute kernels does not hold them up (csrc/pack.cu)
+            pending.append(feed)
+        else:
+            eng.prefetch(feed)
 
     fn.engine = eng
     fn.prefetch = prefetch
