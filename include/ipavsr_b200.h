@@ -234,6 +234,12 @@ int ipavsr_batch_gather(const float* data, int ldd, const int64_t* integral_lens
  * to permute / un-permute utterances of the other streams, masks, targets and outputs. */
 int ipavsr_gather_rows(const void* src, int64_t src_pitch_bytes, void* dst, int64_t dst_pitch_bytes, int row_bytes,
                        const int32_t* idx, const void* fill_row, int64_t rows, void* stream);
+/* The pack step for a PINNED HOST stream, done by the copy engines instead of a kernel: utterance order_host[i] (N, T, row
+ * layout, utt_pitch_bytes apart) -> packed rows offsets_host[i] .. offsets_host[i+1]-1 of dst, plus the zero row at
+ * offsets_host[N].  order_host / offsets_host are HOST arrays (N and N+1 entries).  One asynchronous copy per utterance:
+ * no SM is taken from the kernels it overlaps with. */
+int ipavsr_upload_ragged(const void* host_src, int64_t utt_pitch_bytes, int64_t row_bytes, void* dst, int64_t dst_pitch_bytes,
+                         const int32_t* order_host, const int64_t* offsets_host, int N, void* stream);
 /* out[c] (+)= sum of X[r, c] over the rows with (rowmask[r] != 0) != invert: the gradient of the shared constant row
  * (all padding rows of the expanded bottleneck) in the backward of that expansion. */
 int ipavsr_colsum_masked(const float* X, int ldx, const uint8_t* rowmask, int invert, float* out, int M, int N,

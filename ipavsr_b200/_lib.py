@@ -87,6 +87,7 @@ _SIGS = {
     'ipavsr_align_fill': (I, [P, I, P, I, P, P, P, I, I, I64, P]),
     'ipavsr_gather_rows': (I, [P, I64, P, I64, I, P, P, I64, P]),
     'ipavsr_colsum_masked': (I, [P, I, P, I, P, I, I, I, P]),
+    'ipavsr_upload_ragged': (I, [P, I64, I64, P, I64, P, P, I, P]),
     'ipavsr_debug_gemm_timestamps': (I, [P]),
     'ipavsr_debug_lstm_timestamps': (I, [P]),
     'ipavsr_fill': (I, [P, U64, F, P]),

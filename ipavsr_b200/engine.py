@@ -281,6 +281,7 @@ class _PackPlan(object):
         mask4 = np.zeros((N * T + 3) // 4 * 4, dtype=np.uint8)
         mask4[:N * T] = mask
         self.order_host, self.perm_host, self.lens_sorted, self.offsets_host = order, perm, ls, off
+        self.order32 = np.ascontiguousarray(order.astype(np.int32))
         # active_rows[t] = number of (sorted) utterances longer than t: the rows a per-step recurrent GEMM has to compute
         self.active_rows = np.ascontiguousarray((ls[None, :] > np.arange(T)[:, None]).sum(1).astype(np.int32))
         self.tables = [('pack', pack), ('valid', valid), ('unpack', unpack), ('perm', perm), ('unperm', unperm),
@@ -464,6 +465,9 @@ class Engine(object):
         self._layer_lo = {}
         for key, (off, rows, cols, ld) in self.arena.tensors.items():
             self._layer_lo[key[0]] = min(self._layer_lo.get(key[0], off), off)
+        # pinned host streams of an encoder: 'dma' = one copy-engine transfer per utterance, 'gather' = the row-gather
+        # kernel reading host memory (fewer driver calls, but its CTAs keep SMs from the compute kernels)
+        self.host_upload = os.environ.get('IPAVSR_HOST_UPLOAD', 'dma')
         self._dct_basis = {}         # (image shape, K) -> DCT basis of a derived DCT stream
         self._plans = []             # most recent _PackPlans [(key, plan)]
         self._plan_pins = []         # ring of pinned staging tensors [(tensor, event)]
@@ -832,6 +836,14 @@ class Engine(object):
         """Input stream `t` ((N, T, F) float32 torch tensor: device, or pinned host) in the plan's layout: packed rows for
         an encoder input, whole utterances in sorted order otherwise."""
         N, T, F = t.shape
+        if l in self.pack_in and not t.is_cuda and self.host_upload == 'dma':
+            # pinned host stream: one copy-engine transfer per utterance (valid frames only) — no SM is taken from the
+            # compute kernels the upload overlaps with
+            out = self.new(plan.M + 1, F, zero=(_ld8(F) != F))
+            _lib.call('ipavsr_upload_ragged', t.data_ptr(), 4 * T * F, 4 * F, out.ptr, 4 * out.ld,
+                      plan.order32.ctypes.data_as(C.c_void_p), plan.offsets_host.ctypes.data_as(C.c_void_p), N,
+                      stream if stream is not None else self.stream)
+            return out
         if l in self.pack_in:
             return self._gather(t.data_ptr(), F, plan.M + 1, F, plan.pack, stream=stream)
         return self._gather(t.data_ptr(), F, N * T, F, plan.perm, stream=stream)

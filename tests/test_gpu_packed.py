@@ -253,9 +253,12 @@ def test_packed_run_matches_padded_run_and_oracle(name, fusiontype, device_input
             assert err < 1e-4, (p.name, err)
 
 
-def test_packed_pinned_host_inputs_and_prefetch():
-    """Pinned host streams are gathered by the kernel straight from host memory (ragged upload); prefetch stages the same
-    plan; pageable inputs take the copy-then-gather route.  All three give the same probabilities."""
+@pytest.mark.parametrize('upload', ['dma', 'gather'])
+def test_packed_pinned_host_inputs_and_prefetch(upload, monkeypatch):
+    """Pinned host streams are uploaded ragged — one copy-engine transfer per utterance ('dma', the default) or the gather
+    kernel reading host memory ('gather'); prefetch (immediate and deferred) stages the same plan; pageable inputs take the
+    copy-then-gather route.  All give the same probabilities."""
+    monkeypatch.setenv('IPAVSR_HOST_UPLOAD', upload)
     from ipavsr_b200.function import function, tensor as T
     spec, net, feed, mask, y, dm, win = _case('adenet_v2', 5, 'concat', N=64, T=20)
     ins = MU.input_layers(net)
@@ -270,8 +273,16 @@ def test_packed_pinned_host_inputs_and_prefetch():
     assert len(val.engine._prefetched) == 1
     c = val(hx, hm, hd, win)
     assert len(val.engine._prefetched) == 0
+    val.prefetch(hx, hm, hd, win, defer=True)          # staged by the next call, behind its own kernels
+    assert len(val.engine._prefetched) == 0
+    c2 = val(hx, hm, hd, win)
+    assert len(val.engine._prefetched) == 1
+    c3 = val(hx, hm, hd, win)
+    assert len(val.engine._prefetched) == 0
     np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(a, c)
+    np.testing.assert_array_equal(a, c2)
+    np.testing.assert_array_equal(a, c3)
     assert np.abs(a - ref).max() / np.abs(ref).max() < 1e-4
     # a mask that is not a prefix mask falls back to the padded layout (and still matches the oracle)
     m2 = mask.copy()
