@@ -14,8 +14,8 @@ process per GPU (torchrun) shards utterances and all-reduces the flat gradient a
 One JSON line on stdout (rank 0):
   value        utterances/s with the three padded streams already resident in HBM (device-timed, max over ranks);
   e2e          the same step through the public `function(...)` callable from pinned HOST memory: every step uploads the
-               valid frames of the raw stream (ragged gather straight from pinned memory), computes the diff-image and
-               DCT(+deltas) streams on the device from it (ipavsr_b200.derived) and reads the loss back;
+               valid frames of the raw stream (ragged copy-engine transfer), computes the diff-image and DCT(+deltas)
+               streams on the device from it (ipavsr_b200.derived) and reads the loss back;
   roofline     the dominant kernel (encoder fc1 GEMM on the packed rows of the batch) timed live, vs the measured bf16 peak;
   rooflines    BASELINE config 4: the streaming kernels over 1 048 576 frames vs the measured HBM bandwidth;
   inference_4stream   BASELINE config 5: adenet_4stream, 4096 utterances sharded over the ranks, no collective;
@@ -685,9 +685,9 @@ def main():
                 'config': config, 'clocks': clk.summary(),
                 'e2e': {'value': e2e, 'unit': 'utterances/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 12,
                         'ms_per_step': ms_e2e,
-                        'inputs': 'pinned host raw stream (valid frames gathered over PCIe by ipavsr_gather_rows), targets and '
-                                  'index tables; diff-image and DCT+delta streams computed on the device from it '
-                                  '(ipavsr_b200.derived); loss read back'},
+                        'inputs': 'pinned host raw stream (valid frames only, one batched copy-engine transfer per step: '
+                                  'ipavsr_upload_ragged), targets and index tables; diff-image and DCT+delta streams '
+                                  'computed on the device from it (ipavsr_b200.derived); loss read back'},
                 'e2e_padded_streams': {'value': args.batch * world / (ms_e2e_p * 1e-3), 'unit': 'utterances/s',
                                        'ms_per_step': ms_e2e_p, 'h2d_bytes_per_step': args.batch * T_FRAMES * (sum(STREAM_DIMS) * 4 + 4),
                                        'note': "the reference's call convention: three padded host streams per step"},

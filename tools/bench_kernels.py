@@ -194,7 +194,7 @@ if 'gemm' in only:
             report('gemm %-18s %dx%dx%d %s' % (name, M, N, K, label), ms, flops=fl)
         del A, B, Cm, ah, al, bh, bl
 if 'lstm' in only:
-    shapes = ((26, 250, 150), (512, 250, 150), (512, 500, 150), (4096, 250, 150))
+    shapes = ((26, 250, 150), (512, 250, 150), (26, 500, 150), (512, 500, 150), (4096, 250, 150))
     if os.environ.get('IPAVSR_BENCH_LSTM_N'):
         shapes = tuple((int(n), 250, 150) for n in os.environ['IPAVSR_BENCH_LSTM_N'].split(','))
     for N, H, I in shapes:
@@ -235,6 +235,24 @@ if 'lstm' in only:
                                           ci.data_ptr(), mask.data_ptr(), gates.data_ptr(), cell.data_ptr(), dg.data_ptr(), dpeep.data_ptr(), dci.data_ptr(), dhi.data_ptr(),
                                           N, T, H, ldh, 0, 5.0, 0, None, None, None, None, ws.data_ptr(), nbytes, st()), reps=5)
             report('lstm_bwd_f16 N=%d H=%d tcgen05' % (N, H), ms, flops=2.0 * N * T * H * 4 * H, extra='  %.2f us/step' % (ms * 1e3 / T))
+        if H > 256 and lib.ipavsr_lstm_steps_supported(N, T, H, 4 * H):
+            # wide layers: one tensor-core GEMM + one cell kernel per step (csrc/lstm_steps_tc.cu), unsorted lengths
+            wh, wl = torch.empty(H, 4 * H, dtype=torch.float16, device='cuda'), torch.empty(H, 4 * H, dtype=torch.float16, device='cuda')
+            sc = torch.zeros(2, device='cuda')
+            _lib.call('ipavsr_f16_split', whid.data_ptr(), 4 * H, H, 4 * H, wh.data_ptr(), wl.data_ptr(), 4 * H, sc.data_ptr(), sc.data_ptr() + 4, 0, st())
+            sb = lib.ipavsr_lstm_steps_workspace_bytes(N, T, H)
+            sws = torch.empty((sb + 3) // 4, device='cuda')
+            dgh, dgl = torch.empty(N * T, 4 * H, dtype=torch.float16, device='cuda'), torch.empty(N * T, 4 * H, dtype=torch.float16, device='cuda')
+            dge = torch.zeros(2, dtype=torch.int32, device='cuda')
+            ms = timeit(lambda: _lib.call('ipavsr_lstm_fwd_f16_steps', xw.data_ptr(), whid.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4, 4 * H,
+                                          peep.data_ptr(), ci.data_ptr(), hi.data_ptr(), mask.data_ptr(), out.data_ptr(), gates.data_ptr(), cell.data_ptr(),
+                                          hprev.data_ptr(), N, T, H, ldh, 0, None, sws.data_ptr(), sb, st()), reps=5)
+            report('lstm_fwd_f16_steps N=%d H=%d tcgen05 GEMM per step (train saves)' % (N, H), ms, flops=2.0 * N * T * H * 4 * H, extra='  %.2f us/step' % (ms * 1e3 / T))
+            ms = timeit(lambda: _lib.call('ipavsr_lstm_bwd_f16_steps', dout.data_ptr(), whid.data_ptr(), wh.data_ptr(), wl.data_ptr(), sc.data_ptr() + 4, 4 * H,
+                                          peep.data_ptr(), ci.data_ptr(), mask.data_ptr(), gates.data_ptr(), cell.data_ptr(), dg.data_ptr(), dpeep.data_ptr(),
+                                          dci.data_ptr(), dhi.data_ptr(), N, T, H, ldh, 0, 5.0, 0, dgh.data_ptr(), dgl.data_ptr(), dge.data_ptr(), None,
+                                          sws.data_ptr(), sb, st()), reps=5)
+            report('lstm_bwd_f16_steps N=%d H=%d tcgen05 GEMM per step' % (N, H), ms, flops=2.0 * N * T * H * 4 * H, extra='  %.2f us/step' % (ms * 1e3 / T))
         del xw, out, hprev, gates, cell, dout, dg, ws
 if 'opt' in only:
     n = 24 * 1024 * 1024
