@@ -698,7 +698,8 @@ def main():
                                    'note': 'device-resident step at %d utterances per GPU' % alt},
                 'batch_26': {'value': 26 * world / (ms_26 * 1e-3), 'unit': 'utterances/s', 'ms_per_step': ms_26,
                              'gpu_launches_per_step': int(launches_26) // max(args.steps, 1),
-                             'note': "the reference's own batch (avletters/trimodal.py:356-359): launch-bound"},
+                             'note': "the reference's own batch (avletters/trimodal.py:356-359); launch-bound when run "
+                                     "eagerly, so forward + loss + backward replay one CUDA graph per step"},
                 'rooflines': rooflines, 'inference_4stream': inference, 'configs': configs}
         print(json.dumps(line))
     if world > 1:

@@ -60,6 +60,8 @@ int ipavsr_version(void);
 const char* ipavsr_source_hash(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches counter) */
 uint64_t ipavsr_launch_count(void);
+/* a replayed CUDA graph launches the kernels that were counted while it was captured: the host side adds them per replay */
+void ipavsr_launch_count_add(uint64_t n);
 /* device properties the host side sizes grids with; returns 0 or a negative code */
 int ipavsr_device_info(int* sm_count, int* cc_major, int* cc_minor, int* max_smem_optin);
 

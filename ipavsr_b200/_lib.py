@@ -24,6 +24,7 @@ _SIGS = {
     'ipavsr_version': (I, []),
     'ipavsr_source_hash': (C.c_char_p, []),
     'ipavsr_launch_count': (U64, []),
+    'ipavsr_launch_count_add': (None, [U64]),
     'ipavsr_device_info': (I, [P, P, P, P]),
     'ipavsr_gemm': (I, [I, I, I, I, I, I, P, I, P, I, P, I, P, I, I, P, U64, P]),
     'ipavsr_gemm_workspace_bytes': (U64, [I, I, I, I, I, I]),
@@ -140,6 +141,14 @@ def check(status, what=''):
                                                             msg.decode() if msg else '?'))
 
 
+_fn_cache = {}
+
+
 def call(name, *args):
     """Invoke a status-returning entry point and raise on failure."""
-    check(getattr(load(), name)(*args), name)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    rc = fn(*args)
+    if rc != 0:
+        check(rc, name)

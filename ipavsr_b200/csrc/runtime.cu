@@ -35,6 +35,7 @@ int ipavsr_version(void) { return 200; }
 #endif
 const char* ipavsr_source_hash(void) { return IPAVSR_SRC_HASH; }
 uint64_t ipavsr_launch_count(void) { return ipavsr::g_launches.load(); }
+void ipavsr_launch_count_add(uint64_t n) { ipavsr::count_launch(n); }
 
 int ipavsr_device_info(int* sm, int* major, int* minor, int* max_smem_optin) {
   int dev = 0;

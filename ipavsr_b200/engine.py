@@ -489,6 +489,10 @@ class Engine(object):
         self._copy_stream = None
         self._prefetched = []
         self._c14 = None
+        self._st_pin = None
+        # CUDA graphs for launch-bound small batches: 'auto' (default) | 'off'  (IPAVSR_GRAPH=0)
+        self.graph_mode = 'off' if os.environ.get('IPAVSR_GRAPH', '1') == '0' else 'auto'
+        self._graphs, self._graph_failed = {}, False
         self._zpool, self._zpos = None, 0
         self._opool, self._opos = None, 0
         # fp16 hi/lo of sigmoid/tanh outputs written by the GEMM epilogue itself (static scale 2^14, coalesced through the
@@ -502,7 +506,14 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------------
     @property
     def stream(self):
+        # torch.cuda.current_stream costs ~7 us and a step asks ~120 times: the handle is pinned while a forward / backward
+        # walk runs on one stream (the staging code, which switches streams, passes its handles explicitly)
+        if self._st_pin is not None:
+            return self._st_pin
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _pin_stream(self, on):
+        self._st_pin = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if on else None
 
     def new(self, rows, cols, zero=False):
         ld = _ld8(cols)
@@ -756,11 +767,12 @@ class Engine(object):
                 derived = True             # computed on the device from the packed frames of its source: needs the plan
             elif l is not ml and (len(inputs[l].shape) != 3 or tuple(inputs[l].shape[:2]) != (N, T)):
                 return None
+        if self.packed_mode != 'force' and not derived and N * T < 2048:
+            return None                    # small batches are launch-bound: the extra row movers would not pay
         lens = self._lens_of(mask)
         if lens is None or N == 0:
             return None
-        if (self.packed_mode != 'force' and not derived and
-                (N * T < 2048 or (N * T - int(lens.sum())) * 16 < N * T)):
+        if self.packed_mode != 'force' and not derived and (N * T - int(lens.sum())) * 16 < N * T:
             return None
         key = (T, lens.tobytes())
         for i, (k, plan) in enumerate(self._plans):
@@ -1127,13 +1139,17 @@ class Engine(object):
         run.window = int(window) if window is not None else 0
         run.deterministic = deterministic
         ar = self.arena
-        for l in self.layers:
-            if _Nvtx.on:
-                torch.cuda.nvtx.range_push('fwd %s' % (l.name or type(l).__name__))
-            self._forward_layer(run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn)
-            if _Nvtx.on:
-                torch.cuda.nvtx.range_pop()
-        return self._forward_finish(run)
+        self._pin_stream(True)
+        try:
+            for l in self.layers:
+                if _Nvtx.on:
+                    torch.cuda.nvtx.range_push('fwd %s' % (l.name or type(l).__name__))
+                self._forward_layer(run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn)
+                if _Nvtx.on:
+                    torch.cuda.nvtx.range_pop()
+            return self._forward_finish(run)
+        finally:
+            self._pin_stream(False)
 
     def _forward_layer(self, run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn):
         lib, st, ar = self.lib, self.stream, self.arena
@@ -1736,6 +1752,13 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------------
     def loss_and_backward(self, run, probs, loss, y, mask, count=None):
         """Runs the loss kernel (writes loss sum into the gradient arena tail) and the full backward."""
+        self._pin_stream(True)
+        try:
+            return self._loss_and_backward(run, probs, loss, y, mask, count)
+        finally:
+            self._pin_stream(False)
+
+    def _loss_and_backward(self, run, probs, loss, y, mask, count=None):
         st, ar = self.stream, self.arena
         plan = run.plan
         # a packed / length-sorted run computes the loss in its own utterance order: targets follow, the mask is the plan's
@@ -1874,6 +1897,89 @@ class Engine(object):
             torch.distributed.all_reduce(both, group=self.world[2])
         h = both.cpu().numpy()
         return np.float32(h[0] / h[1])
+
+    # ------------------------------------------------------------------------------------------------
+    # small batches: the whole forward + loss + backward as ONE CUDA graph launch
+    # ------------------------------------------------------------------------------------------------
+    def graph_eligible(self, inputs, y, deterministic, l2):
+        """The reference's own batches (26 utterances, `avletters/trimodal.py:356-359`; 10, `oulu/bimodal.py:360`) are
+        launch-bound: ~140 launches whose enqueue takes the host longer than the device needs to run them.  Such a step is
+        captured once per input shape (static input buffers, everything else allocated inside the capture) and replayed;
+        the optimiser update stays outside the graph (its bias-correction scalar changes every step).  Not for: batches large
+        enough to pack (the plan changes the shapes per batch), random dropout (the counter would be baked in), data
+        parallelism, L2 penalties, derived or host-chunked inputs."""
+        if self.graph_mode == 'off' or self._graph_failed or self.world is not None or l2 or len(self.mask_layers) > 1:
+            return False
+        if not deterministic and any(isinstance(l, L.DropoutLayer) for l in self.layers):
+            return False
+        rows = None
+        for l in self.input_layers:
+            a = inputs[l]
+            if isinstance(a, Derived) or not hasattr(a, 'shape') or len(a.shape) not in (2, 3):
+                return False
+            rows = int(a.shape[0]) * int(a.shape[1])
+        if rows is None or rows >= 2048 or self.packed_mode == 'force':
+            return False
+        return y is not None and hasattr(y, 'shape')
+
+    def _to_static(self, buf, a):
+        if isinstance(a, torch.Tensor):
+            buf.copy_(a.to(buf.dtype) if a.dtype != buf.dtype else a, non_blocking=True)
+        else:
+            buf.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(
+                {torch.float32: np.float32, torch.uint8: np.uint8, torch.int32: np.int32}[buf.dtype], copy=False))),
+                non_blocking=True)
+
+    def graph_step(self, inputs, window, y, mask_layer, loss, deterministic):
+        """forward + loss + backward of one small batch by replaying its CUDA graph (captured on first use per shape).
+        Returns False when the capture failed (the caller then runs the eager path)."""
+        key = (tuple((id(l), tuple(int(d) for d in inputs[l].shape)) for l in self.input_layers), int(window or 0), loss,
+               tuple(int(d) for d in y.shape), bool(deterministic))
+        ent = self._graphs.get(key)
+        if ent is None:
+            bufs = {}
+            for l in self.input_layers:
+                dt = torch.uint8 if l in self.mask_layers else torch.float32
+                bufs[l] = torch.empty(tuple(int(d) for d in inputs[l].shape), dtype=dt, device=self.device)
+            ybuf = torch.empty(tuple(int(d) for d in y.shape), dtype=torch.int32, device=self.device)
+            for l in self.input_layers:
+                self._to_static(bufs[l], inputs[l])
+            self._to_static(ybuf, y)
+            mbuf = bufs[mask_layer] if mask_layer is not None else None
+
+            def body():
+                run, out = self.forward(bufs, window, deterministic, train=True)
+                self.loss_and_backward(run, out, loss, ybuf, mbuf, count=None)
+
+            try:
+                # one eager pass first: lazily created state (fp16 arenas, workspaces, constants, function attributes) must
+                # exist before the capture and live outside the graph's memory pool
+                body()
+                self.arena.split_dirty = True        # the captured step refreshes the operand split of the parameters
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                n0 = int(self.lib.ipavsr_launch_count())
+                with torch.cuda.graph(g):
+                    body()
+                ent = (g, bufs, ybuf, int(self.lib.ipavsr_launch_count()) - n0)
+                self._graphs[key] = ent
+                if len(self._graphs) > 8:
+                    self._graphs.pop(next(iter(self._graphs)))
+            except Exception as e:                    # capture not possible here: stay on the eager path for good
+                self._graph_failed = True
+                import warnings
+                warnings.warn('ipavsr_b200: CUDA-graph capture of the small-batch step failed (%s); running eagerly' % (e,))
+                torch.cuda.synchronize(self.device)
+                return False
+            # the eager pass and the capture left valid gradients of THIS batch in the arena only via the eager pass;
+            # replay once so that the state is exactly what a replayed step leaves
+        g, bufs, ybuf, nlaunch = ent
+        for l in self.input_layers:
+            self._to_static(bufs[l], inputs[l])
+        self._to_static(ybuf, y)
+        g.replay()
+        self.lib.ipavsr_launch_count_add(nlaunch)      # the kernels of this repository inside the replayed graph
+        return True
 
     def allreduce_grads(self):
         if self.world is None:

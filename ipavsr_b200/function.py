@@ -179,15 +179,20 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         if not train:
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
             return eng.loss_only(out, loss_name, y, mask, l2=l2)
-        with _Nvtx('forward'):
-            run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks, targets=y)
-        eng._ar_enabled = not l2          # an L2 penalty is added to the finished gradient arena: all-reduce afterwards
-        with _Nvtx('loss + backward'):
-            eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
-                                  count=float(np.asarray(mask).sum()) if (mask is not None and not hasattr(mask, 'is_cuda'))
-                                  else None)
-            if l2:
-                eng.l2_penalty(l2)
+        graphed = False
+        if not dropout_masks and eng.graph_eligible(feed, y, pred.deterministic, l2):
+            with _Nvtx('forward + loss + backward (CUDA graph)'):
+                graphed = eng.graph_step(feed, window, y, mask_layer, loss_name, pred.deterministic)
+        if not graphed:
+            with _Nvtx('forward'):
+                run, out = eng.forward(feed, window, pred.deterministic, train=True, dropout_masks=dropout_masks, targets=y)
+            eng._ar_enabled = not l2          # an L2 penalty is added to the finished gradient arena: all-reduce afterwards
+            with _Nvtx('loss + backward'):
+                eng.loss_and_backward(run, out, loss_name, y, run.vals[mask_layer] if mask_layer is not None else None,
+                                      count=float(np.asarray(mask).sum())
+                                      if (mask is not None and not hasattr(mask, 'is_cuda')) else None)
+                if l2:
+                    eng.l2_penalty(l2)
         with _Nvtx('gradient all-reduce'):
             eng.allreduce_grads()
         u = updates

@@ -129,3 +129,44 @@ def test_default_mode_is_the_tensor_core_mode():
     import os
     if 'IPAVSR_GEMM_MODE' not in os.environ:
         assert Engine(net).gemm_mode == 4        # f16x3: the benchmarked arithmetic is the shipped default
+
+
+@pytest.mark.parametrize('name,fusiontype', [('adenet_v2', 'concat'), ('adenet_v1', 'sum'), ('deltanet', 'sum')])
+def test_small_batch_cuda_graph_step_matches_eager(name, fusiontype, monkeypatch):
+    """Launch-bound small batches (the reference's own batch sizes) replay ONE CUDA graph per step; losses and parameters
+    after several steps on changing batches equal the eager path's."""
+    from ipavsr_b200.custom.objectives import categorical_crossentropy
+
+    def run(graph):
+        monkeypatch.setenv('IPAVSR_GRAPH', '1' if graph else '0')
+        spec, net, feed, mask, y = _net(seed=12, name=name, fusiontype=fusiontype, N=10, T=12)
+        level = spec['level']
+        ins = MU.input_layers(net)
+        pred = L.get_output(net, deterministic=False)
+        params = L.get_all_params(net, trainable=True)
+        if level == 'frame':
+            tg = T.imatrix('t')
+            cost = temporal_softmax_loss(pred, tg, ins['mask'].input_var)
+        else:
+            tg = T.ivector('t')
+            cost = T.mean(categorical_crossentropy(pred, tg))
+        order = [ins[n].input_var for n in spec['names']]
+        train = function([order[0], tg, ins['mask'].input_var] + order[1:] + [T.iscalar('w')], cost,
+                         updates=U.adam(cost, params, learning_rate=1e-2))
+        assert (train.engine.graph_mode == 'auto') == graph
+        rng = np.random.default_rng(99)
+        losses = []
+        for step in range(4):
+            xs, m2, _ = MU.make_feed(rng, 10, 12, spec['dims'])          # a new batch (new lengths) every step
+            yy = rng.integers(0, 7, size=10).astype('int32')
+            yy = yy if level == 'seq' else np.repeat(yy[:, None], 12, 1).astype('int32')
+            losses.append(float(train(xs[0], yy, m2, *xs[1:], 3)))
+        if graph:
+            assert len(train.engine._graphs) == 1 and not train.engine._graph_failed
+        return losses, [p.get_value() for p in params]
+
+    l_g, p_g = run(True)
+    l_e, p_e = run(False)
+    np.testing.assert_allclose(l_g, l_e, rtol=2e-5)
+    for a, b in zip(p_g, p_e):
+        assert np.abs(a - b).max() <= 2e-4 * max(1.0, np.abs(b).max())
