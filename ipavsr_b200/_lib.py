@@ -90,6 +90,7 @@ _SIGS = {
     'ipavsr_colsum_masked': (I, [P, I, P, I, P, I, I, I, P]),
     'ipavsr_upload_ragged': (I, [P, I64, I64, P, I64, P, P, I, P]),
     'ipavsr_debug_gemm_timestamps': (I, [P]),
+    'ipavsr_debug_gemm_persistent_launches': (U64, []),
     'ipavsr_debug_lstm_timestamps': (I, [P]),
     'ipavsr_fill': (I, [P, U64, F, P]),
     'ipavsr_tf32_split': (I, [P, P, P, U64, P]),

@@ -41,6 +41,13 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 
 int sm_count();
 
+// fp16 operand pairs of the three-product GEMM mode (f16split.cu): x 2^e = hi + lo / F16_LO_SCALE.  With the scale 1 the
+// cross products lo*hi, hi*lo are on the scale of hi*hi, so one TMEM accumulator takes all three (gemm_f16p.cu) and a
+// 256-wide tile can be double-buffered in the 512 TMEM columns.  The price is dynamic range: lo lives in the fp16
+// subnormals for elements below 2^-18 of the tensor's maximum, i.e. the pair holds x to max(2^-22 |x|, 2^-39 max|x|).
+constexpr float F16_LO_SCALE = 1.0f;
+constexpr float F16_LO_INV = 1.0f / F16_LO_SCALE;
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float act_fwd(float z, int act) {

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) prep_f16_kernel(const float* __restrict__
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         h[k] = __float2half_rn(v[k]);
-        l[k] = __float2half_rn((v[k] - __half2float(h[k])) * 2048.0f);
+        l[k] = __float2half_rn((v[k] - __half2float(h[k])) * F16_LO_SCALE);
       }
       *reinterpret_cast<uint2*>(hi + (size_t)r * ldo + c) = *reinterpret_cast<const uint2*>(h);
       *reinterpret_cast<uint2*>(lo + (size_t)r * ldo + c) = *reinterpret_cast<const uint2*>(l);

@@ -29,7 +29,7 @@ __device__ __forceinline__ void f16_scale_factors(int e, float& s1, float& s2) {
 __device__ __forceinline__ void f16_hi_lo(float x, float s1, float s2, __half& hi, __half& lo) {
   const float xs = x * s1 * s2;
   hi = __float2half_rn(xs);
-  lo = __float2half_rn((xs - __half2float(hi)) * 2048.0f);
+  lo = __float2half_rn((xs - __half2float(hi)) * F16_LO_SCALE);
 }
 
 __device__ __forceinline__ void atomic_max_pos(float* addr, float v) {

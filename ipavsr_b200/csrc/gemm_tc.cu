@@ -26,230 +26,17 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace ipavsr {
-
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                 // floats per stage along K (one 128-byte swizzle row); 64 halves in f16 mode
-constexpr int TC_THREADS = 256;
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// ---- CTA-pair (cta_group::2) variants: the leader CTA (cluster rank 0) issues one MMA for both SMs; each CTA's TMA
-// loads complete on the LEADER's full barrier; the leader's commit arrives on the barriers of both CTAs.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
-  uint32_t out;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
-  return out;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
-                                                int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
-      "[%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit_cg2(uint64_t* bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"((uint16_t)3)
-      : "memory");
-}
-template <bool F16>
-__device__ __forceinline__ void tcgen05_mma_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                uint32_t accumulate) {
-  if (F16)
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-  else
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Epilogue nonlinearities.  sigmoid as 1 / (1 + 2^(-x log2 e)) with ex2.approx / rcp.approx (each <= 2 ulp): relative
-// error ~3e-7 + |x| * 4e-8, far inside the GEMM's own rounding; saturates correctly (ex2 -> 0 / inf, rcp(inf) = 0).
-__device__ __forceinline__ float sigmoid_fast(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
-}
-__device__ __forceinline__ float act_epi(float z, int act) {
-  return act == IPAVSR_ACT_SIGMOID ? sigmoid_fast(z) : act_fwd(z, act);
-}
-
-// a = hi + lo (+ ~2^-22 |a|) with hi and lo exactly representable in tf32
-__device__ __forceinline__ void tf32_hi_lo(float a, float& hi, float& lo) {
-  uint32_t hb, lb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
-  hi = __uint_as_float(hb);
-  float rem = a - hi;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
-  lo = __uint_as_float(lb);
-}
-
-// UMMA shared-memory matrix descriptor (version 1).  Address/offset fields in 16-byte units.
-// layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B — the only layout the tensor core accepts
-// for MN-major 32-bit (tf32) operands; its TMA counterpart is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;     // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-// instruction descriptor: D=f32, A=B=tf32 (format 2, kind::tf32) or fp16 (format 0, kind::f16), majors, N>>3, M>>4
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, bool f16, int m = TC_BM) {
-  return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((a_mn ? 1u : 0u) << 15) |
-         ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-struct TcParams {
-  int M, N, K;
-  float* C;
-  int ldc;
-  const float* bias;
-  int act;
-  int accumulate;
-  int kb_per_split;   // k-blocks (of TC_BK) per split
-  int splits;
-  float* Chi;         // optional: rna_tf32(C) and rna_tf32(C - Chi), same ldc (operands of a following 3xTF32 GEMM)
-  float* Clo;
-  const int32_t* expA;   // f16 mode: per-tensor scale exponents of the operands (device), result *= 2^-(eA+eB)
-  const int32_t* expB;
-  float* amax;           // optional (device): atomic max of |C| over the written elements (feeds the next fp16 split)
-  uint16_t* C16hi;       // optional: fp16 hi/lo split of C with the STATIC scale 2^c16_exp (outputs with a known bound,
-  uint16_t* C16lo;       //           e.g. sigmoid/tanh: |C| <= 1 -> exponent 14), same leading dimension as C
-  int c16_exp;
-  unsigned long long* dbg;   // optional (device): per-CTA phase timestamps (globaltimer ns), see tools/gemm_phases.py
-};
-
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // CG = 2: a CTA pair (cluster (2,1,1), same TPC) computes a 256 x BN tile with one cta_group::2 MMA per k-step: each CTA
 // keeps its own 128 rows of A and HALF of the B tile in shared memory (the tensor core of each SM reads both halves),
 // which cuts the L2->SM operand traffic per flop by a third and the shared-memory reads per MMA by a third.
-template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// OCC = 2: two CTAs (of different pairs) resident per SM, each with half of the shared memory and of the TMEM columns, so
+// that the epilogue of one tile runs under the mainloop of the other (the 128-wide pair tile of the fp16 mode).
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG, int OCC = 1>
+__global__ void __launch_bounds__(TC_THREADS, OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, TcParams p) {
   constexpr int BKE = F16 ? 2 * TC_BK : TC_BK;        // elements per stage along K (128 bytes either way)
@@ -261,15 +48,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   static_assert(BNL % MNBOX == 0, "the per-CTA share of the B tile must be whole TMA boxes");
   constexpr int NOPER = (NPROD == 3) ? 2 : 1;         // hi (+ lo) copies of each operand
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
-  constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
+  constexpr int SMEM_BUDGET = (OCC == 2 ? 100 : 200) * 1024;
+  constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES < 8 ? SMEM_BUDGET / STAGE_BYTES : 8;
   static_assert(STAGES >= 2, "need at least a double buffer");
   static_assert(!F16 || NPROD == 3, "the fp16 path is the three-product mode");
   // TMEM accumulators.  The tensor core adds into its fp32 accumulator with truncation, so the error grows with the
   // number of accumulations into one accumulator.  In the 3xTF32 mode the tiny cross terms (lo*hi + hi*lo) get their
   // own accumulator and the hi*hi terms are spread round-robin (by k-block) over NMAIN accumulators; the epilogue sums
   // them in registers with round-to-nearest.
-  constexpr int TMEM_COLS = (NPROD == 3) ? 512 : BN;
-  constexpr int NMAIN = (NPROD == 3) ? (512 / BN - 1) : 1;
+  constexpr int TMEM_COLS = (NPROD == 3) ? 512 / OCC : BN;
+  constexpr int NMAIN = (NPROD == 3) ? (TMEM_COLS / BN - 1) : 1;
+  static_assert(NMAIN >= 1, "main + cross accumulators must fit the TMEM share of this CTA");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -416,7 +205,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t t_cross = tmem_base + (uint32_t)(NMAIN * BN);
           const uint32_t t_main = tmem_base + (uint32_t)((kb % NMAIN) * BN);
           const uint32_t main_acc = (kb < NMAIN && k == 0) ? 0u : 1u;
-          if (CG == 2) {
+          if (F16 && p.oneacc) {
+            if (CG == 2) {
+              tcgen05_mma_cg2<F16>(t_main, a_lo, b_hi, idesc, main_acc);
+              tcgen05_mma_cg2<F16>(t_main, a_hi, b_lo, idesc, 1u);
+              tcgen05_mma_cg2<F16>(t_main, a_hi, b_hi, idesc, 1u);
+            } else {
+              tcgen05_mma_f16(t_main, a_lo, b_hi, idesc, main_acc);
+              tcgen05_mma_f16(t_main, a_hi, b_lo, idesc, 1u);
+              tcgen05_mma_f16(t_main, a_hi, b_hi, idesc, 1u);
+            }
+          } else if (CG == 2) {
             tcgen05_mma_cg2<F16>(t_cross, a_lo, b_hi, idesc, first);
             tcgen05_mma_cg2<F16>(t_cross, a_hi, b_lo, idesc, 1u);
             tcgen05_mma_cg2<F16>(t_main, a_hi, b_hi, idesc, main_acc);
@@ -467,7 +266,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       ms1 = __int_as_float((127 + e1) << 23);
       ms2 = __int_as_float((127 + e2) << 23);
     }
-    const float cs1 = F16 ? ms1 * (1.0f / 2048.0f) : 1.f;
+    const float cs1 = F16 ? ms1 * (F16_LO_INV) : 1.f;
     float tile_max = 0.f;
     const bool fast_ok = vec && !split && num_kb > 0;      // warp-uniform
 #pragma unroll 1
@@ -479,7 +278,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float v[32];
         if (NPROD == 3) {
           float u[32];
-          tmem_ld32_issue(lane_base + (uint32_t)(NMAIN * BN), v);           // cross terms
+          if (F16 && p.oneacc) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          } else {
+            tmem_ld32_issue(lane_base + (uint32_t)(NMAIN * BN), v);         // cross terms
+          }
           tmem_ld32_issue(lane_base, u);                                    // first main accumulator
           tmem_ld_wait();
           if (F16) {
@@ -575,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     h[j] = __float2half_rn(ov[j]);
-                    l[j] = __float2half_rn((ov[j] - __half2float(h[j])) * 2048.0f);
+                    l[j] = __float2half_rn((ov[j] - __half2float(h[j])) * F16_LO_SCALE);
                   }
                   const size_t off = (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj;
                   *reinterpret_cast<uint2*>(p.C16hi + off) = *reinterpret_cast<const uint2*>(h);
@@ -609,10 +413,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float v[32];
       if (num_kb > 0) {
         if (NPROD == 3) {
-          tmem_ld32(lane_base + (uint32_t)(NMAIN * BN), v);                 // cross terms first (smallest)
+          if (F16 && p.oneacc) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          } else {
+            tmem_ld32(lane_base + (uint32_t)(NMAIN * BN), v);               // cross terms first (smallest)
+          }
           if (F16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= (1.0f / 2048.0f);          // lo carries a 2^11 scale
+            for (int j = 0; j < 32; ++j) v[j] *= (F16_LO_INV);          // lo carries a 2^11 scale
           }
           const int used = num_kb < NMAIN ? num_kb : NMAIN;
 #pragma unroll 1
@@ -689,7 +498,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                   const __half h = __float2half_rn(xs);
                   reinterpret_cast<__half*>(p.C16hi)[(size_t)row * p.ldc + col + j] = h;
                   reinterpret_cast<__half*>(p.C16lo)[(size_t)row * p.ldc + col + j] =
-                      __float2half_rn((xs - __half2float(h)) * 2048.0f);
+                      __float2half_rn((xs - __half2float(h)) * F16_LO_SCALE);
                 }
               }
             } else {
@@ -713,7 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const __half h = __float2half_rn(xs);
                     reinterpret_cast<__half*>(p.C16hi)[(size_t)row * p.ldc + col + j] = h;
                     reinterpret_cast<__half*>(p.C16lo)[(size_t)row * p.ldc + col + j] =
-                        __float2half_rn((xs - __half2float(h)) * 2048.0f);
+                        __float2half_rn((xs - __half2float(h)) * F16_LO_SCALE);
                   }
                 }
             }
@@ -777,7 +586,7 @@ static EncodeTiledFn get_encode() {
 // 2-D row-major tensor [outer][inner] (fp32, or fp16 when f16) with row stride ld elements; box {box_inner, box_outer};
 // 128B swizzle (the 32B-atom variant for MN-major 32-bit operands)
 static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                    uint32_t box_outer, bool mn_major, bool f16 = false) {
+                    uint32_t box_outer, bool mn_major, bool f16 = false, bool sw64 = false) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
     set_error("gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -789,7 +598,8 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   (mn_major && !f16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   sw64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                        : ((mn_major && !f16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -826,15 +636,16 @@ uint64_t gemm_tc_workspace_bytes(int mode, int transA, int transB, int M, int N,
   return 2 * (a + b) * sizeof(float) * 2;   // x2 head-room for leading dimensions up to twice the logical width
 }
 
-template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG>
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG, int OCC = 1>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo,
                      TcParams p, cudaStream_t st) {
   constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = (BN / CG) * TC_BK * 4;
   constexpr int NOPER = (NPROD == 3) ? 2 : 1;
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
-  constexpr int STAGES = (200 * 1024) / STAGE_BYTES < 8 ? (200 * 1024) / STAGE_BYTES : 8;
+  constexpr int SMEM_BUDGET = (OCC == 2 ? 100 : 200) * 1024;
+  constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES < 8 ? SMEM_BUDGET / STAGE_BYTES : 8;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD, F16, CG>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD, F16, CG, OCC>;
   IPAVSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int mtiles = (p.M + TC_BM - 1) / TC_BM;
   dim3 grid((p.N + BN - 1) / BN, mtiles, p.splits);
@@ -860,16 +671,18 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUten
   return IPAVSR_OK;
 }
 
-template <int BN, int NPROD, bool F16, int CG>
+template <int BN, int NPROD, bool F16, int CG, int OCC = 1>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
                           const CUtensorMap& mBlo, TcParams p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
-  return launch_tc<BN, true, true, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
+  return launch_tc<BN, true, true, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
 }
 
 int amax_launch(const float* x, int ldx, int rows, int cols, float* amax, cudaStream_t st);   // f16split.cu
+int gemm_f16p_launch(int bn, int kb, bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mAlo,
+                     const CUtensorMap& mB, const CUtensorMap& mBlo, const TcParams& p, cudaStream_t st);   // gemm_f16p.cu
 
 // core: operands already split (3xTF32: fp32 hi/lo arrays; f16: fp16 hi/lo arrays + scale exponents) or raw (TF32:
 // *lo ignored).  kind: 0 = single TF32, 1 = 3xTF32, 2 = fp16 three-product.
@@ -880,37 +693,59 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
   const bool x3 = kind != 0, f16 = kind == 2;
   const bool a_mn = transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;     // B stored [K,N]: N contiguous
-  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  // IPAVSR_GEMM_OCC: 0 = 256-wide pair tiles, one CTA per SM; 1 = 128-wide pair tiles, one CTA per SM; 2 = 128-wide pair
+  // tiles, two CTAs per SM (one tile's epilogue under the other's mainloop)
+  static int occ_env = -1;
+  if (occ_env < 0) {
+    const char* e = getenv("IPAVSR_GEMM_OCC");
+    occ_env = e ? atoi(e) : 0;
+  }
   const int bke = f16 ? 2 * TC_BK : TC_BK;      // elements per k-block = 128 bytes
   const int mnbox = f16 ? 64 : 32;              // MN-major box: 128 bytes of M/N, bke k-rows
   CUtensorMap mA, mAlo, mB, mBlo;
   int rc;
-  // A: K-major -> tensor [M][K], box {bke, 128};  MN-major -> tensor [K][M], box {mnbox, bke}
-  if (!a_mn) {
-    if ((rc = make_map(&mA, Ahi, K, M, lda, bke, TC_BM, false, f16))) return rc;
-    if ((rc = make_map(&mAlo, Alo, K, M, lda, bke, TC_BM, false, f16))) return rc;
-  } else {
-    if ((rc = make_map(&mA, Ahi, M, K, lda, mnbox, bke, true, f16))) return rc;
-    if ((rc = make_map(&mAlo, Alo, M, K, lda, mnbox, bke, true, f16))) return rc;
-  }
+  // A: K-major -> tensor [M][K], box {kb, 128};  MN-major -> tensor [K][M], box {mnbox, kb};  B likewise with its share
+  // bnl of the tile's columns.  kb = elements along K per stage: one 128-byte swizzle row, or half of one (64-byte
+  // swizzle for the K-major operand) in the persistent kernel's deep ring.
+  auto make_maps = [&](int kb, int bnl) -> int {
+    const bool sw64 = f16 && kb == 32;
+    int r;
+    if (!a_mn) {
+      if ((r = make_map(&mA, Ahi, K, M, lda, kb, TC_BM, false, f16, sw64))) return r;
+      if ((r = make_map(&mAlo, Alo, K, M, lda, kb, TC_BM, false, f16, sw64))) return r;
+    } else {
+      if ((r = make_map(&mA, Ahi, M, K, lda, mnbox, kb, true, f16))) return r;
+      if ((r = make_map(&mAlo, Alo, M, K, lda, mnbox, kb, true, f16))) return r;
+    }
+    if (!b_mn) {
+      if ((r = make_map(&mB, Bhi, K, N, ldb, kb, bnl, false, f16, sw64))) return r;
+      if ((r = make_map(&mBlo, Blo, K, N, ldb, kb, bnl, false, f16, sw64))) return r;
+    } else {
+      if ((r = make_map(&mB, Bhi, N, K, ldb, mnbox, kb, true, f16))) return r;
+      if ((r = make_map(&mBlo, Blo, N, K, ldb, mnbox, kb, true, f16))) return r;
+    }
+    return IPAVSR_OK;
+  };
   // CTA pairs (cta_group::2) for wide outputs with at least two row tiles; IPAVSR_GEMM_CG=1 forces single-CTA tiles
   static int cg_env = -1;
   if (cg_env < 0) {
     const char* e = getenv("IPAVSR_GEMM_CG");
     cg_env = (e && e[0] == '1') ? 1 : 2;
   }
-  const int cg = (BN == 256 && M > TC_BM && cg_env == 2) ? 2 : 1;
-  if (!b_mn) {
-    if ((rc = make_map(&mB, Bhi, K, N, ldb, bke, BN / cg, false, f16))) return rc;
-    if ((rc = make_map(&mBlo, Blo, K, N, ldb, bke, BN / cg, false, f16))) return rc;
-  } else {
-    if ((rc = make_map(&mB, Bhi, N, K, ldb, mnbox, bke, true, f16))) return rc;
-    if ((rc = make_map(&mBlo, Blo, N, K, ldb, mnbox, bke, true, f16))) return rc;
-  }
+  int cg = (BN == 256 && M > TC_BM && cg_env == 2) ? 2 : 1;
+  int occ = 1;
+  if (f16 && cg == 2 && occ_env >= 1) { BN = 128; occ = occ_env >= 2 ? 2 : 1; }
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
   p.Chi = Chi; p.Clo = Clo; p.expA = expA; p.expB = expB; p.amax = amax;
   p.dbg = g_gemm_dbg;
+  static int oneacc_env = -1;
+  if (oneacc_env < 0) {
+    const char* e = getenv("IPAVSR_GEMM_ONEACC");
+    oneacc_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  p.oneacc = (f16 && oneacc_env) ? 1 : 0;
   p.C16hi = C16hi; p.C16lo = C16lo; p.c16_exp = c16_exp;
   const int num_kb = (K + bke - 1) / bke;
   const int tiles = ((M + TC_BM * cg - 1) / (TC_BM * cg)) * cg * ((N + BN - 1) / BN);
@@ -950,11 +785,54 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
   p.splits = splits;
   if (splits > 1 && !accumulate)
     IPAVSR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+  // Persistent kernel (gemm_f16p.cu) for the big fp16 products: IPAVSR_GEMM_PERSIST = 1 (256-wide tiles, one accumulator),
+  // 2 (128-wide tiles, main + cross accumulators), 0 = off; used when the product has more work units than CTA pairs.
+  static int persist_env = -1, persist_min = 0;
+  if (persist_env < 0) {
+    const char* e = getenv("IPAVSR_GEMM_PERSIST");
+    persist_env = e ? atoi(e) : 1;
+    const char* m = getenv("IPAVSR_GEMM_PERSIST_MIN");
+    persist_min = m ? atoi(m) : 4 * (sm_count() / 2);
+  }
+  // (measured, 13 325 rows: 424-unit products gain 12-18 %; with 3 units per pair the scheduler only adds latency, and the
+  //  atomic epilogue of a k-split is slower next to the operand stream than in the tile-per-pair kernel's own phase)
+  static int persist_split = -1;
+  if (persist_split < 0) {
+    const char* e = getenv("IPAVSR_GEMM_PERSIST_SPLIT");
+    persist_split = (e && e[0] == '1') ? 1 : 0;
+  }
+  // small K: the unit is epilogue-bound and the tile-per-pair kernel's lockstep epilogue does as well (K = 150: 41 vs 51 us)
+  const bool use_p = f16 && BN == 256 && cg == 2 && occ == 1 && persist_env > 0 && tiles / 2 * splits >= persist_min &&
+                     (splits == 1 || persist_split) && num_kb / splits >= 8;
+  if (use_p) {
+    // halves along K per stage of the persistent kernel: 64 = 3 stages of 64 KB, 32 = 6 stages of 32 KB.  Measured at
+    // 13 325 rows: no gain from the deeper ring (fc1 forward 0.143 ms either way) and the 64-byte-swizzled K-major tiles
+    // cost the product with two K-major operands 27 % (fc2 dgrad 0.129 -> 0.164 ms): 64 stays the default.
+    static int persist_kb = -1;
+    if (persist_kb < 0) {
+      const char* e = getenv("IPAVSR_GEMM_PERSIST_KB");
+      persist_kb = (e && atoi(e) == 32) ? 32 : 64;
+    }
+    const int pbn = persist_env == 2 ? 128 : 256;
+    const int pkb = pbn == 256 ? persist_kb : 64;
+    if ((rc = make_maps(pkb, pbn / 2))) return rc;
+    TcParams pp = p;
+    pp.kb_per_split = p.kb_per_split * (bke / pkb);      // counted in blocks of pkb
+    rc = gemm_f16p_launch(pbn, pkb, a_mn, b_mn, mA, mAlo, mB, mBlo, pp, st);
+    if (rc != -1000) {                  // -1000: declined (no unit counter left for a captured launch)
+      if (rc) return rc;
+      if (amax != nullptr && splits > 1) return amax_launch(C, ldc, M, N, amax, st);
+      return IPAVSR_OK;
+    }
+  }
+  if ((rc = make_maps(bke, BN / cg))) return rc;
 #define IPAVSR_TC_DISPATCH(BNV, CGV)                                                                  \
   rc = f16 ? dispatch_major<BNV, 3, true, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)                 \
            : (x3 ? dispatch_major<BNV, 3, false, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)          \
                  : dispatch_major<BNV, 1, false, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st))
   if (BN == 64) { IPAVSR_TC_DISPATCH(64, 1); }
+  else if (BN == 128 && cg == 2 && occ == 2) { rc = dispatch_major<128, 3, true, 2, 2>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st); }
+  else if (BN == 128 && cg == 2) { rc = dispatch_major<128, 3, true, 2, 1>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st); }
   else if (BN == 128) { IPAVSR_TC_DISPATCH(128, 1); }
   else if (cg == 2) { IPAVSR_TC_DISPATCH(256, 2); }
   else { IPAVSR_TC_DISPATCH(256, 1); }

@@ -33,7 +33,7 @@ namespace {
 __device__ __forceinline__ void split16(float x, float scale, __half& hi, __half& lo) {
   const float xs = x * scale;
   hi = __float2half_rn(xs);
-  lo = __float2half_rn((xs - __half2float(hi)) * 2048.0f);
+  lo = __float2half_rn((xs - __half2float(hi)) * F16_LO_SCALE);
 }
 
 struct SCell {

@@ -300,7 +300,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
       const int j = i / Kpad, k = i - j * Kpad;
       const float xs = (k < H ? hid_init[k] : 0.f) * hs;
       const __half hi = __float2half_rn(xs);
-      const __half lo = __float2half_rn((xs - __half2float(hi)) * 2048.0f);
+      const __half lo = __float2half_rn((xs - __half2float(hi)) * F16_LO_SCALE);
       const uint32_t off = (uint32_t)(k >> 5) * 2048u + q_sw64(j, k & 31);
       *reinterpret_cast<__half*>(sH + off) = hi;
       *reinterpret_cast<__half*>(sH + HBYTES + off) = lo;
@@ -431,7 +431,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
 #pragma unroll
         for (int j = 0; j < QC; ++j) {
           const float cr = KSTEPS >= QCROSS ? c0[j] + c1[j] : c0[j];
-          a[j] = fmaf(cr, 1.0f / 2048.0f, c2[j]);
+          a[j] = fmaf(cr, F16_LO_INV, c2[j]);
           if (nacc > 1) a[j] += c3[j];
         }
 #pragma unroll 1
@@ -489,7 +489,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
         // h_{t+1} of (utterance j0 + 4i + g, unit ul) into the staging chunk, fp16 hi/lo, SWIZZLE_64B K-major layout
         const float xs = (u_ok ? r.h : 0.f) * hs;
         const __half hi = __float2half_rn(xs);
-        const __half lo = __float2half_rn((xs - __half2float(hi)) * 2048.0f);
+        const __half lo = __float2half_rn((xs - __half2float(hi)) * F16_LO_SCALE);
         const uint32_t off = q_sw64(j0 + 4 * i + g, ul);
         *reinterpret_cast<__half*>(stg + off) = hi;
         *reinterpret_cast<__half*>(stg + 2048 + off) = lo;
@@ -768,7 +768,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           h[q] = __float2half_rn(v[q]);
-          l[q] = __float2half_rn((v[q] - __half2float(h[q])) * 2048.0f);
+          l[q] = __float2half_rn((v[q] - __half2float(h[q])) * F16_LO_SCALE);
         }
         if (dg_hi != nullptr && n_ok[i] && u_ok) {
           // the same fp16 hi/lo pair is the split of dgates for the weight-gradient GEMMs that follow: no split pass
@@ -808,7 +808,7 @@ lstm_bwd_tc_kernel(const __grid_constant__ CUtensorMap mapWhi, const __grid_cons
             q_tmem_wait();
 #pragma unroll
             for (int j = 0; j < QC; ++j)
-              a[j] = (fmaf(c0[j] + c1[j], 1.0f / 2048.0f, a[j]) + c2[j] + (c3[j] + c4[j])) * ms1 * ms2;
+              a[j] = (fmaf(c0[j] + c1[j], F16_LO_INV, a[j]) + c2[j] + (c3[j] + c4[j])) * ms1 * ms2;
 #pragma unroll
             for (int j = 0; j < QC; j += 4)
               asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)(hf * QC + j) * 4u),

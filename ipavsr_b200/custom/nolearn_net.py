@@ -131,8 +131,18 @@ class NeuralNet(object):
         return self
 
     def predict_proba(self, X):
+        """nolearn's `predict_proba`: the rows are independent, so the matrix goes up ONCE, runs in large row chunks and comes
+        back in one copy (nolearn's own 128-row batches would each cost an upload, a launch-bound forward and a download).
+        A CUDA tensor stays on the device: the result is a CUDA tensor."""
+        import torch
         self.initialize()
-        X = np.asarray(X, dtype=np.float32)
-        return np.vstack([self.predict_iter_(self._rows(X[s])) for s in self._batches(len(X))])
+        dev = self.predict_iter_.engine.device
+        on_dev = isinstance(X, torch.Tensor) and X.is_cuda
+        Xd = X.to(torch.float32) if on_dev else torch.from_numpy(np.ascontiguousarray(np.asarray(X), dtype=np.float32)).to(dev)
+        Xd = Xd.reshape(Xd.shape[0], -1).contiguous()
+        chunk = 16384
+        outs = [self.predict_iter_(Xd[i:i + chunk].unsqueeze(1), device_output=True) for i in range(0, len(Xd), chunk)]
+        res = torch.cat(outs, dim=0) if len(outs) != 1 else outs[0]
+        return res if on_dev else res.cpu().numpy()
 
     predict = predict_proba

@@ -523,7 +523,10 @@ class Engine(object):
 
     def _side_stream(self):
         if not self._side:
-            self._side = [torch.cuda.Stream(device=self.device) for _ in range(3)]
+            # the recurrence kernels run here: latency chains the main stream ends up waiting for, so their CTAs go first
+            # whenever SMs free up (IPAVSR_SIDE_PRIORITY=0: same priority as the main stream)
+            pr = -1 if os.environ.get('IPAVSR_SIDE_PRIORITY', '1') == '1' else 0
+            self._side = [torch.cuda.Stream(device=self.device, priority=pr) for _ in range(3)]
         st = self._side[self._side_next % len(self._side)]
         self._side_next += 1
         return st

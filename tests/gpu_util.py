@@ -32,6 +32,9 @@ def call(name, *args):
     _lib.call(name, *args)
 
 
+F16_LO_SCALE = 1.0      # x 2^e = hi + lo / F16_LO_SCALE (csrc/common.cuh)
+
+
 def host(t):
     torch.cuda.synchronize()
     return t.detach().cpu().numpy()

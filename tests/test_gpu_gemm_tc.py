@@ -75,6 +75,25 @@ def test_f16x3_matches_fp32_parity(M, N, K, ta, tb):
     assert err < 1.5e-6, err
 
 
+# ---- persistent kernel (csrc/gemm_f16p.cu): products with >= 4 work units per CTA pair and no k-split -------------------
+# All three partial products accumulate in ONE fp32 TMEM accumulator (three truncating adds per k-step instead of one): its
+# stated tolerance is 4e-6 of |A|max |B|max sqrt(K) (measured 1.3e-6 at K = 1200, 2.7e-6 at K = 4096) against 1.5e-6 for
+# the tile-per-pair kernel with its separate cross-term accumulator.
+@pytest.mark.parametrize('ta,tb,M,N,K', [(0, 0, 13325, 2000, 1200), (0, 1, 13325, 2000, 1000), (1, 0, 9728, 2000, 1024),
+                                         (1, 1, 9728, 2000, 1024), (0, 0, 9700, 2040, 4000)])
+def test_f16x3_persistent_kernel(ta, tb, M, N, K):
+    before = G.lib().ipavsr_debug_gemm_persistent_launches()
+    err = _run(4, ta, tb, M, N, K)
+    assert err < 4e-6, err
+    assert G.lib().ipavsr_debug_gemm_persistent_launches() == before + 1        # the persistent kernel ran this product
+
+
+@pytest.mark.parametrize('act,acc,use_bias', [(1, 0, True), (2, 1, True), (0, 1, False), (3, 0, True)])
+def test_f16x3_persistent_epilogue_variants(act, acc, use_bias):
+    err = _run(4, 0, 0, 13325, 2000, 1200, act, acc, use_bias)
+    assert err < 5e-4, err
+
+
 @pytest.mark.parametrize('sa,sb', [(1e-7, 1.0), (3e4, 1e-3), (1e-12, 1e-9), (1e6, 1e5)])
 def test_f16x3_scale_invariance(sa, sb):
     """Per-tensor power-of-two scales: operand magnitudes far outside the fp16 range keep fp32-class accuracy."""
@@ -109,9 +128,11 @@ def test_f16x3_presplit_api_and_amax():
     e = G.host(exps)
     assert 2.0 ** 14 <= am[0] * 2.0 ** int(e[0]) < 2.0 ** 15 and 2.0 ** 14 <= am[1] * 2.0 ** int(e[1]) < 2.0 ** 15
     # the pair reproduces the scaled value to ~2^-22
-    rec = (G.host(ah).astype(np.float64) + G.host(al).astype(np.float64) / 2048.0) / 2.0 ** int(e[0])
-    big = np.abs(A) > np.abs(A).max() * 2.0 ** -28
+    rec = (G.host(ah).astype(np.float64) + G.host(al).astype(np.float64) / G.F16_LO_SCALE) / 2.0 ** int(e[0])
+    # (the unscaled lo half sits in the fp16 subnormals below 2^-18 of the tensor's maximum: an absolute floor there)
+    big = np.abs(A) > np.abs(A).max() * 2.0 ** -17
     assert (np.abs(rec - A)[big] <= np.abs(A)[big] * 2.0 ** -21).all()
+    assert (np.abs(rec - A) <= np.maximum(np.abs(A) * 2.0 ** -21, np.abs(A).max() * 2.0 ** -38)).all()
     dC = G.zeros((M, N))
     G.call('ipavsr_gemm_f16x3', 0, 0, M, N, K, ah.data_ptr(), al.data_ptr(), K, exps.data_ptr(), bh.data_ptr(),
            bl.data_ptr(), N, exps.data_ptr() + 4, dC.data_ptr(), N, None, 0, 0, amax.data_ptr() + 8, None, None, 0, G.stream())

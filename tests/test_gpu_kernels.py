@@ -326,7 +326,7 @@ def test_lstm_bwd_tensor_core(N, T, H, peep, backwards, scale):
             dgv = G.host(d_dg).astype(np.float64)
             assert G.relerr(G.host(d_db), dgv.sum(0)) < 1e-5
             ex = int(G.host(dge)[0])
-            rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / 2048.0) / 2.0 ** ex
+            rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / G.F16_LO_SCALE) / 2.0 ** ex
             assert np.abs(rec - dgv).max() <= max(np.abs(dgv).max() * 2.0 ** -20, 1e-12)
         else:
             G.call('ipavsr_lstm_bwd', d_dout.data_ptr(), d_whid.data_ptr(), G.ptr(d_peep), d_ci.data_ptr(), d_mask.data_ptr(),
@@ -781,7 +781,7 @@ def test_lstm_steps_tensor_core(N, T, H, peep, backwards, sorted_lens):
     dgv = G.host(d_dg).astype(np.float64)
     assert np.isfinite(dgv).all()
     ex = int(G.host(dge)[0])
-    rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / 2048.0) / 2.0 ** ex
+    rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / G.F16_LO_SCALE) / 2.0 ** ex
     assert np.abs(rec - dgv).max() <= max(np.abs(dgv).max() * 2.0 ** -20, 1e-12)
     dG = G.deinterleave_gates(G.host(d_dg), H).astype(np.float64)
     tol = 3e-4

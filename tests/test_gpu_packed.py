@@ -170,7 +170,7 @@ def test_lstm_tensor_core_skips_masked_frames(kind, N, T, H, peep, backwards):
     dgv = G.host(d_dg).astype(np.float64)
     assert np.isfinite(dgv).all()
     ex = int(G.host(dge)[0])
-    rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / 2048.0) / 2.0 ** ex
+    rec = (G.host(dgh).astype(np.float64) + G.host(dgl).astype(np.float64) / G.F16_LO_SCALE) / 2.0 ** ex
     assert np.abs(rec - dgv).max() <= max(np.abs(dgv).max() * 2.0 ** -20, 1e-12)
     dG = G.deinterleave_gates(G.host(d_dg), H).astype(np.float64)
     tol = 3e-4
