@@ -640,19 +640,23 @@ def main():
         gemm_ms = time_kernel(run, flush, reps=10, warm=3)
         peak = float(peaks.get('bf16_tflops', 1590.0))
         achieved = 2.0 * M * N * K / (gemm_ms * 1e-3) / 1e12
-        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/r02_ncu_full_summary.md):
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/r02c_ncu_gemm_summary.md):
         # same N and K, and M within 5 % of the rows timed here (the packed row count follows the random lengths)
-        traffic, traffic_at = None, None
+        traffic, traffic_at, ncu_ent = None, None, None
         try:
             prof = json.load(open(os.path.join(ROOT, 'profiles', 'r02_dominant_kernel.json')))
             for ent in prof.get('entries', [prof]):
                 sh = ent.get('shape') or [0, 0, 0]
                 if ent.get('mode') == args.mode and sh[1:] == [N, K] and abs(sh[0] - M) <= 0.05 * M:
                     traffic, traffic_at = ent.get('dram_bytes_per_launch'), sh
+                    ncu_ent = ent
         except Exception:
             pass
-        roofline = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel: encoder fc1 GEMM %dx%dx%d (%s) on the packed rows of a '
-                                                  '%d-utterance batch' % (M, N, K, args.mode, args.batch),
+        p_before = _lib.load().ipavsr_debug_gemm_persistent_launches()
+        run()
+        kname = 'gemm_f16p_kernel (persistent)' if _lib.load().ipavsr_debug_gemm_persistent_launches() > p_before else 'gemm_tc_kernel'
+        roofline = {'bound': 'tensor', 'kernel': '%s: encoder fc1 GEMM %dx%dx%d (%s) on the packed rows of a '
+                                                  '%d-utterance batch' % (kname, M, N, K, args.mode, args.batch),
                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                     'traffic_measured_at_shape': traffic_at,
                     'peak_source': 'MEASURED_PEAKS.json bf16 burst' if peaks else 'fallback 1.59 PFLOP/s',
@@ -662,6 +666,10 @@ def main():
                                        'is half of bf16, so the ceiling of this mode is 1/6 of the bf16 peak'}.get(
                                  args.mode, 'algorithmic FLOPs'),
                     'ms_per_launch': gemm_ms}
+        if ncu_ent is not None:
+            roofline['ncu'] = {'kernel': ncu_ent.get('kernel'), 'tensor_pipe_active_pct': ncu_ent.get('tensor_pipe_active_pct'),
+                               'sm_clock_ghz_during_kernel': ncu_ent.get('sm_clock_ghz'), 'time_us': ncu_ent.get('time_us'),
+                               'source': 'profiles/r02c_ncu_gemm_summary.md (committed ncu --set full capture, not this run)'}
         del A, B, Cm, flush
         if not args.no_extras and world == 1:
             hbm = float(peaks.get('hbm_gbs', 6650.0))
