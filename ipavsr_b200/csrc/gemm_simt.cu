@@ -278,4 +278,24 @@ int gemm_simt(int transA, int transB, int M, int N, int K, const float* A, int l
   return launch_simt<128, 128>(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, act, accumulate, st);
 }
 
+// out[k] (+)= sum_j W[k * ldw + j] * s[j]  (k < rows, j < cols): one warp per row of W.  The d(hid_init) product of the
+// LSTM backward after the sum over the utterances (lstm*.cu): 1 x 4H by 4H x H.
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ W, int ldw, const float* __restrict__ s,
+                                                        float* __restrict__ out, int rows, int cols, int accumulate) {
+  const int warp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* w = W + (size_t)warp * ldw;
+  float acc = 0.f;
+  for (int j = lane; j < cols; j += 32) acc = fmaf(__ldg(w + j), __ldg(s + j), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[warp] = accumulate ? out[warp] + acc : acc;
+}
+
+int gemv_rows(const float* W, int ldw, const float* s, float* out, int rows, int cols, int accumulate, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return IPAVSR_OK;
+  gemv_rows_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(W, ldw, s, out, rows, cols, accumulate);
+  IPAVSR_LAUNCH_CHECK();
+  return IPAVSR_OK;
+}
+
 }  // namespace ipavsr

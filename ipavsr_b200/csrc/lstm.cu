@@ -28,6 +28,7 @@ namespace cg = cooperative_groups;
 
 namespace ipavsr {
 
+int gemv_rows(const float* W, int ldw, const float* s, float* out, int rows, int cols, int accumulate, cudaStream_t st);
 int gemm_simt(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
               float* C, int ldc, const float* bias, int act, int accumulate, cudaStream_t st);
 
@@ -835,11 +836,14 @@ int ipavsr_lstm_bwd(const float* dout, const float* w_hid, const float* peep, co
     dc_fin = dc_buf;
     dh_fin = dh_pass;
   }
-  // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step
-  int rc = gemm_simt(0, 1, N, H, 4 * H, dgates + (size_t)t_first * 4 * H, T * 4 * H, w_hid, 4 * H, dh_fin, H, nullptr,
-                     IPAVSR_ACT_LINEAR, 1, st);
+  // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step; the
+  // product is linear, so it is taken after the sum over the utterances (one column sum + a vector-matrix product)
+  float* dg_sum = rec;                // the recurrent pre-activation region is free once the steps are done
+  int rc = ipavsr_colsum(dgates + (size_t)t_first * 4 * H, T * 4 * H, dg_sum, N, 4 * H, 0, stream);
   if (rc) return rc;
   rc = ipavsr_colsum(dh_fin, H, dhid_init, N, H, 1, stream);
+  if (rc) return rc;
+  rc = gemv_rows(w_hid, 4 * H, dg_sum, dhid_init, H, 4 * H, 1, st);
   if (rc) return rc;
   rc = ipavsr_colsum(dc_fin, H, dcell_init, N, H, 1, stream);
   return rc;

@@ -20,6 +20,7 @@
 
 namespace ipavsr {
 
+int gemv_rows(const float* W, int ldw, const float* s, float* out, int rows, int cols, int accumulate, cudaStream_t st);
 int gemm_simt(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
               float* C, int ldc, const float* bias, int act, int accumulate, cudaStream_t st);
 int gemm_tc_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* Ahi, const uint16_t* Alo, int lda,
@@ -398,17 +399,16 @@ int ipavsr_lstm_bwd_f16_steps(const float* dout, const float* w_hid, const uint1
       int rc = ipavsr_colsum(w.ppart + k * NH, H, dpeep + k * H, N, H, 1, stream);
       if (rc) return rc;
     }
-  // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step
+  // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step; the
+  // product is linear, so it is taken after the sum over the utterances (one column sum + a vector-matrix product)
   int rc;
   const size_t off_first = (size_t)t_first * 4 * H;
-  if (gemm_tc_f16_supported(N, H, 4 * H, dg_hi + off_first, T * 4 * H, whid_hi, ldw))
-    rc = gemm_tc_f16x3(0, 1, N, H, 4 * H, dg_hi + off_first, dg_lo + off_first, T * 4 * H, dg_exp, whid_hi, whid_lo, ldw,
-                       whid_exp, w.dh_pass, H, nullptr, IPAVSR_ACT_LINEAR, 1, nullptr, nullptr, nullptr, 0, st);
-  else
-    rc = gemm_simt(0, 1, N, H, 4 * H, dgates + off_first, T * 4 * H, w_hid, 4 * H, w.dh_pass, H, nullptr, IPAVSR_ACT_LINEAR,
-                   1, st);
+  float* dg_sum = w.rec;              // free once the steps are done
+  rc = ipavsr_colsum(dgates + off_first, T * 4 * H, dg_sum, N, 4 * H, 0, stream);
   if (rc) return rc;
   rc = ipavsr_colsum(w.dh_pass, H, dhid_init, N, H, 1, stream);
+  if (rc) return rc;
+  rc = gemv_rows(w_hid, 4 * H, dg_sum, dhid_init, H, 4 * H, 1, st);
   if (rc) return rc;
   return ipavsr_colsum(w.dc, H, dcell_init, N, H, 1, stream);
 }

@@ -30,6 +30,7 @@
 
 namespace ipavsr {
 
+int gemv_rows(const float* W, int ldw, const float* s, float* out, int rows, int cols, int accumulate, cudaStream_t st);
 int gemm_simt(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
               float* C, int ldc, const float* bias, int act, int accumulate, cudaStream_t st);
 int gemm_tc_f16x3(int transA, int transB, int M, int N, int K, const uint16_t* Ahi, const uint16_t* Alo, int lda,
@@ -1028,19 +1029,20 @@ int ipavsr_lstm_bwd_f16(const float* dout, const float* w_hid, const uint16_t* w
                                  cell, dgates, dpeep, dc_fin, dh_fin, N, T, H, ldh, backwards, clip, eg, db, dg_hi, dg_lo,
                                  dg_exp));
   count_launch();
-  // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step
+  // d(hid_init) = sum_n [ dg_first W_hid^T + dh_pass ],  d(cell_init) = sum_n dc_prev at the first processed step.
+  // Only the sum over the utterances is wanted, so the product is taken AFTER the sum (it is linear): one column sum of
+  // the first processed frame's gate gradients (rows n, stride T*4H) and a 1 x 4H by 4H x H vector-matrix product, in
+  // place of the N x H x 4H GEMM this used to run on the critical path of every backward step (95 us at H = 250: its
+  // output pitch H = 250 took the GEMM's scalar epilogue).
   const int t_first = backwards ? T - 1 : 0;
   int rc;
   const size_t off_first = (size_t)t_first * 4 * H;
-  if (dg_hi != nullptr && gemm_tc_f16_supported(N, H, 4 * H, dg_hi + off_first, T * 4 * H, whid_hi, ldw))
-    // the kernel left the fp16 split of dgates behind: the rows of the first processed frame (stride T*4H) are the A operand
-    rc = gemm_tc_f16x3(0, 1, N, H, 4 * H, dg_hi + off_first, dg_lo + off_first, T * 4 * H, dg_exp, whid_hi, whid_lo, ldw,
-                       whid_exp, dh_fin, H, nullptr, IPAVSR_ACT_LINEAR, 1, nullptr, nullptr, nullptr, 0, st);
-  else
-    rc = gemm_simt(0, 1, N, H, 4 * H, dgates + off_first, T * 4 * H, w_hid, 4 * H, dh_fin, H, nullptr, IPAVSR_ACT_LINEAR, 1,
-                   st);
+  float* dg_sum = dh_fin + (size_t)N * H;          // 4H floats behind dc_fin / dh_fin (the workspace holds 8 N H floats)
+  rc = ipavsr_colsum(dgates + off_first, T * 4 * H, dg_sum, N, 4 * H, 0, stream);
   if (rc) return rc;
   rc = ipavsr_colsum(dh_fin, H, dhid_init, N, H, 1, stream);
+  if (rc) return rc;
+  rc = gemv_rows(w_hid, 4 * H, dg_sum, dhid_init, H, 4 * H, 1, st);
   if (rc) return rc;
   return ipavsr_colsum(dc_fin, H, dcell_init, N, H, 1, stream);
 }

@@ -370,6 +370,11 @@ class _Run(object):
         self.pending = {}       # layer -> CUDA event of work still running on a side stream
         self.bwd_ready = {}     # LSTM layer -> (event, dG) launched ahead of the backward walk
         self.keep = []          # buffers that must outlive the side-stream kernels
+        self.use_branches = False   # small batch: every input branch on its own stream (Engine._branch_enter)
+        self.branches_used = set()
+        self.main_stream = None
+        self.branch_joined = {}     # branch -> number of its layers the trunk has already waited for
+        self.branch_done = {}       # branch -> number of its layers issued so far
 
 
 class Engine(object):
@@ -490,6 +495,37 @@ class Engine(object):
         self._prefetched = []
         self._c14 = None
         self._st_pin = None
+        # Branch streams for small batches.  A layer that depends on exactly one non-mask input (a stream's encoder, its
+        # DeltaLayer, its LSTM) belongs to that input's branch; everything behind the fusion is the trunk.  At the
+        # reference's own batch sizes (26 / 10 utterances) no kernel fills the machine, and issuing the branches one after
+        # the other on one stream — where each only starts when the previous one is through — leaves the step 1.5x longer
+        # than its dependency chain (tools/timeline_small.py).  With N*T <= IPAVSR_BRANCH_ROWS every branch runs its
+        # forward and its backward on a stream of its own, ordered against the trunk by events only where data flows
+        # (IPAVSR_BRANCH_STREAMS=0 turns it off).  Large batches keep the single issue order: their GEMMs fill the GPU.
+        self.branch_mode = os.environ.get('IPAVSR_BRANCH_STREAMS', '1') != '0'
+        self.branch_rows = int(os.environ.get('IPAVSR_BRANCH_ROWS', '4096'))
+        deps, self._branch_of = {}, {}
+        for l in self.layers:
+            ins = [i for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]) if i is not None]
+            if isinstance(l, L.InputLayer):
+                deps[l] = frozenset() if l in self.mask_layers else frozenset([l])
+            else:
+                d = frozenset()
+                for i in ins:
+                    d = d | deps.get(i, frozenset())
+                deps[l] = d
+        roots = sorted({next(iter(d)) for d in deps.values() if len(d) == 1}, key=self.layers.index)
+        for l in self.layers:
+            self._branch_of[l] = roots.index(next(iter(deps[l]))) if len(deps[l]) == 1 else None
+        self._n_branches = len(roots)
+        self._branch_streams = []
+        # branch layers whose output (also) feeds the trunk: their gradient arrives from the trunk's stream
+        self._trunk_fed = set()
+        for l in self.layers:
+            if self._branch_of[l] is None:
+                for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
+                    if i is not None and self._branch_of.get(i) is not None:
+                        self._trunk_fed.add(i)
         # CUDA graphs for launch-bound small batches: 'auto' (default) | 'off'  (IPAVSR_GRAPH=0)
         self.graph_mode = 'off' if os.environ.get('IPAVSR_GRAPH', '1') == '0' else 'auto'
         self._graphs, self._graph_failed = {}, False
@@ -549,6 +585,36 @@ class Engine(object):
             self._wait(run, layer)
         for layer, (ev, _) in list(run.bwd_ready.items()):
             torch.cuda.current_stream(self.device).wait_event(ev)
+
+    # ---- branch streams (small batches) ------------------------------------------------------------------------------
+    def _use_branches(self, N, T):
+        return (self.branch_mode and self.world is None and self._n_branches >= 2 and self._n_branches <= 8 and
+                N * T <= self.branch_rows)
+
+    def _branch_enter(self, run, b, sync_from_main):
+        """Makes branch b's stream current (and the pinned kernel stream).  The first entry of a run — and any entry with
+        sync_from_main — orders the branch behind everything queued on the trunk's stream so far."""
+        while len(self._branch_streams) <= b:
+            self._branch_streams.append(torch.cuda.Stream(device=self.device))
+        bs = self._branch_streams[b]
+        if sync_from_main or b not in run.branches_used:
+            ev = torch.cuda.Event()
+            ev.record(run.main_stream)
+            bs.wait_event(ev)
+            run.branches_used.add(b)
+        torch.cuda.set_stream(bs)
+        self._st_pin = C.c_void_p(bs.cuda_stream)
+
+    def _branch_leave(self, run):
+        torch.cuda.set_stream(run.main_stream)
+        self._st_pin = C.c_void_p(run.main_stream.cuda_stream)
+
+    def _branch_join(self, run, b):
+        """The trunk waits for everything queued on branch b so far."""
+        if b in run.branches_used:
+            ev = torch.cuda.Event()
+            ev.record(self._branch_streams[b])
+            run.main_stream.wait_event(ev)
 
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() * 4 < nbytes:
@@ -1143,15 +1209,47 @@ class Engine(object):
         run.deterministic = deterministic
         ar = self.arena
         self._pin_stream(True)
+        run.main_stream = torch.cuda.current_stream(self.device)
+        run.use_branches = self._use_branches(N, T)
+        if run.use_branches:
+            # everything the branches share is created on the trunk's stream BEFORE they fork from it: the scratch pools,
+            # the [1.0, 14] constant, the buffers several LSTMs write their column slice of
+            self._zpool, self._zpos = torch.zeros(16384, dtype=torch.float32, device=self.device), 0
+            self._opool = None
+            self._ones2()
+            self._const14()          # (made once, outside any graph capture: it takes a host scalar)
+            for cl, (_, total) in self.cat_plan.items():
+                run.cat[cl] = (self.new(N * T, total, zero=(_ld8(total) != total)), self._ones2())
         try:
             for l in self.layers:
                 if _Nvtx.on:
                     torch.cuda.nvtx.range_push('fwd %s' % (l.name or type(l).__name__))
-                self._forward_layer(run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn)
+                b = self._branch_of.get(l) if run.use_branches else None
+                if b is not None:
+                    self._branch_enter(run, b, False)
+                    try:
+                        self._forward_layer(run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn)
+                    finally:
+                        self._branch_leave(run)
+                    run.branch_done[b] = run.branch_done.get(b, 0) + 1
+                else:
+                    if run.use_branches:
+                        # a trunk layer waits for the branches it reads from (once per batch of their layers)
+                        for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
+                            bi = self._branch_of.get(i) if i is not None else None
+                            if bi is not None and run.branch_joined.get(bi, 0) < run.branch_done.get(bi, 0):
+                                self._branch_join(run, bi)
+                                run.branch_joined[bi] = run.branch_done[bi]
+                    self._forward_layer(run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn)
                 if _Nvtx.on:
                     torch.cuda.nvtx.range_pop()
+            if run.use_branches:
+                for b in sorted(run.branches_used):       # outputs taken from inside a branch; nothing left running
+                    self._branch_join(run, b)
             return self._forward_finish(run)
         finally:
+            if run.use_branches:
+                self._branch_leave(run)
             self._pin_stream(False)
 
     def _forward_layer(self, run, l, inputs, staged, plan, deterministic, train, dropout_masks, update_bn):
@@ -1473,6 +1571,14 @@ class Engine(object):
         for l in reversed(self.layers):
             in_layers = [i for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)])
                          if i is not None]
+            if run.use_branches:
+                # small batch: the layers of an input branch run their backward on the branch's stream (ordered behind the
+                # trunk where the gradient comes from it); the trunk's own layers on the trunk's
+                self._branch_leave(run)
+                b = self._branch_of.get(l)
+                if b is not None and l in run.grads and not isinstance(l, L.InputLayer):
+                    self._branch_enter(run, b, l in self._trunk_fed)
+                st = self.stream
             if l not in run.grads or isinstance(l, L.InputLayer):
                 self._release(run, in_layers, remaining)
                 continue
@@ -1635,10 +1741,17 @@ class Engine(object):
                 _lib.call('ipavsr_slice_last', g.ptr, g.ld, tgt[0].ptr, tgt[0].ld, N, T, x.cols, 1, acc, st)
             else:
                 raise TypeError('unsupported layer type %s' % type(l).__name__)
-            del run.grads[l]
+            if run.use_branches:
+                run.keep.append(run.grads.pop(l))      # read on another stream than it was allocated on: freed with the run
+            else:
+                del run.grads[l]
             self._release(run, in_layers, remaining)
             if self._ar_hi is not None and l in self._layer_lo:
                 self._ar_flush(self._layer_lo[l])
+        if run.use_branches:
+            self._branch_leave(run)
+            for b in sorted(run.branches_used):
+                self._branch_join(run, b)
         self._join(run)
         if self._ar_hi is not None:
             self._ar_flush(0, final=True)
