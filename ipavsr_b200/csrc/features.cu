@@ -8,9 +8,14 @@
 // Only the no_coeff zigzag positions are ever kept, so the kernel projects each frame onto those basis vectors only:
 // 4*D bytes read and 2*D*K flops per frame (K/2 flop per byte = 15 at K=30: above the FP32-pipe balance point of this
 // part, so dct_project_kernel is FFMA-bound, not HBM-bound).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ipavsr {
+
+// dct_tc.cu: 0 = done, 1 = not a shape of the tensor-core kernel, < 0 = error
+int dct_project_tc(const float* x, int ldx, const float* basis, int ldb, float* out, int ldo, int64_t frames, int D, int K,
+                   cudaStream_t st);
 
 // basis[d*ldb + k] = s(c_k) * cos(pi * (2d+1) * c_k / (2D)),  c_k = cols[k] (or k),  s(0) = sqrt(1/D), s(c>0) = sqrt(2/D)
 // (scipy.fftpack.dct type 2, norm='ortho').  Evaluated in float64 with cospi (exact argument reduction), rounded once.
@@ -358,6 +363,17 @@ int ipavsr_dct_project(const float* x, int ldx, const float* basis, int ldb, flo
   if (frames == 0) return IPAVSR_OK;
   const int64_t tiles = (frames + DCT_TF - 1) / DCT_TF;
   IPAVSR_CHECK_ARG(tiles <= 65535, "at most 65535 * 128 frames per call");
+  // the usual case — a few zig-zag coefficients of long frames — goes to the tensor cores (dct_tc.cu); IPAVSR_DCT_TC=0
+  // keeps the FFMA kernels
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("IPAVSR_DCT_TC");
+    use_tc = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_tc) {
+    const int rc = dct_project_tc(x, ldx, basis, ldb, out, ldo, frames, D, K, S(stream));
+    if (rc <= 0) return rc;           // done (0) or a real error (< 0); 1 = not its shape
+  }
   dim3 grid((K + DCT_TK - 1) / DCT_TK, (unsigned)tiles);
   const bool aligned = D % 4 == 0 && ldx % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)basis & 15) == 0;
   if (aligned)

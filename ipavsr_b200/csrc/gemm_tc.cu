@@ -585,8 +585,8 @@ static EncodeTiledFn get_encode() {
 
 // 2-D row-major tensor [outer][inner] (fp32, or fp16 when f16) with row stride ld elements; box {box_inner, box_outer};
 // 128B swizzle (the 32B-atom variant for MN-major 32-bit operands)
-static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
-                    uint32_t box_outer, bool mn_major, bool f16 = false, bool sw64 = false) {
+int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+             uint32_t box_outer, bool mn_major, bool f16 = false, bool sw64 = false) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) {
     set_error("gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
