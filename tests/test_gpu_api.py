@@ -170,3 +170,48 @@ def test_small_batch_cuda_graph_step_matches_eager(name, fusiontype, monkeypatch
     np.testing.assert_allclose(l_g, l_e, rtol=2e-5)
     for a, b in zip(p_g, p_e):
         assert np.abs(a - b).max() <= 2e-4 * max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize('name,fusiontype', [('adenet_v2', 'concat'), ('adenet_v2', 'sum'), ('adenet_3stream', 'concat'),
+                                             ('adenet_4stream', 'concat')])
+@pytest.mark.parametrize('graph', [False, True])
+def test_branch_streams_match_single_stream(name, fusiontype, graph, monkeypatch):
+    """Small batches run every input branch (encoder -> DeltaLayer -> LSTM) on a stream of its own, forward and backward
+    (Engine._branch_enter); losses and parameters after several steps equal the single-stream issue order.  The kernels
+    and their arguments are the same, so the only admissible difference is the order of the float atomics of k-split
+    weight gradients."""
+    def run(branches):
+        monkeypatch.setenv('IPAVSR_GRAPH', '1' if graph else '0')
+        monkeypatch.setenv('IPAVSR_BRANCH_STREAMS', '1' if branches else '0')
+        spec, net, feed, mask, y = _net(seed=21, name=name, fusiontype=fusiontype, N=10, T=12)
+        ins = MU.input_layers(net)
+        pred = L.get_output(net, deterministic=False)
+        params = L.get_all_params(net, trainable=True)
+        tg = T.imatrix('t') if spec['level'] == 'frame' else T.ivector('t')
+        if spec['level'] == 'frame':
+            cost = temporal_softmax_loss(pred, tg, ins['mask'].input_var)
+        else:
+            from ipavsr_b200.custom.objectives import categorical_crossentropy
+            cost = T.mean(categorical_crossentropy(pred, tg))
+        order = [ins[n].input_var for n in spec['names']]
+        train = function([order[0], tg, ins['mask'].input_var] + order[1:] + [T.iscalar('w')], cost,
+                         updates=U.adam(cost, params, learning_rate=1e-2))
+        eng = train.engine
+        assert eng.branch_mode == branches
+        assert eng._n_branches == len(spec['names'])
+        rng = np.random.default_rng(5)
+        losses = []
+        for step in range(4):
+            xs, m2, _ = MU.make_feed(rng, 10, 12, spec['dims'])
+            yy = rng.integers(0, 7, size=10).astype('int32')
+            yy = yy if spec['level'] == 'seq' else np.repeat(yy[:, None], 12, 1).astype('int32')
+            losses.append(float(train(xs[0], yy, m2, *xs[1:], 3)))
+        if branches:
+            assert len(eng._branch_streams) == eng._n_branches          # every branch really got its stream
+        return losses, [p.get_value() for p in params]
+
+    l_b, p_b = run(True)
+    l_s, p_s = run(False)
+    np.testing.assert_allclose(l_b, l_s, rtol=2e-5)
+    for a, b in zip(p_b, p_s):
+        assert np.abs(a - b).max() <= 2e-4 * max(1.0, np.abs(b).max())

@@ -33,7 +33,10 @@ def test_dct_features_golden_every_method():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('frames,shape,k', [(1, (30, 40), 30), (127, (30, 40), 30), (1000, (26, 44), 30), (300, (30, 50), 45),
-                                            (257, (7, 9), 62), (4096, (30, 40), 30)])
+                                            (257, (7, 9), 62), (4096, (30, 40), 30),
+                                            # the tensor-core kernel (csrc/dct_tc.cu: frames >= 1024, K <= 32): ragged last
+                                            # frame tile, D = 1144 (k tail inside a 32-float block), K < 32 and K = 32
+                                            (5000, (26, 44), 30), (2000, (30, 40), 17), (1500, (30, 40), 32)])
 def test_dct_zigzag_vs_oracle(frames, shape, k):
     P = _pre()
     rng = np.random.default_rng(frames + k)
