@@ -495,15 +495,16 @@ class Engine(object):
         self._prefetched = []
         self._c14 = None
         self._st_pin = None
-        # Branch streams for small batches.  A layer that depends on exactly one non-mask input (a stream's encoder, its
-        # DeltaLayer, its LSTM) belongs to that input's branch; everything behind the fusion is the trunk.  At the
-        # reference's own batch sizes (26 / 10 utterances) no kernel fills the machine, and issuing the branches one after
-        # the other on one stream — where each only starts when the previous one is through — leaves the step 1.5x longer
-        # than its dependency chain (tools/timeline_small.py).  With N*T <= IPAVSR_BRANCH_ROWS every branch runs its
-        # forward and its backward on a stream of its own, ordered against the trunk by events only where data flows
-        # (IPAVSR_BRANCH_STREAMS=0 turns it off).  Large batches keep the single issue order: their GEMMs fill the GPU.
+        # Branch streams.  A layer that depends on exactly one non-mask input (a stream's encoder, its DeltaLayer, its
+        # LSTM) belongs to that input's branch; everything behind the fusion is the trunk.  Every branch runs its forward
+        # and its backward on a stream of its own, ordered against the trunk by events only where data flows
+        # (IPAVSR_BRANCH_STREAMS=0: one issue order on one stream; IPAVSR_BRANCH_ROWS: only for batches of at most that
+        # many frames).  At the reference's own batch sizes (26 / 10 utterances) no kernel fills the machine and the single
+        # issue order leaves the step 1.5x longer than its dependency chain (3.40 -> 2.36 ms, tools/timeline_small.py); at
+        # 512 utterances the other branches' kernels fill the partial last waves of the tile-per-pair GEMMs, the hand-over
+        # gaps between dependent kernels and the SMs a recurrence kernel leaves free (8.2 -> 7.5 ms).
         self.branch_mode = os.environ.get('IPAVSR_BRANCH_STREAMS', '1') != '0'
-        self.branch_rows = int(os.environ.get('IPAVSR_BRANCH_ROWS', '4096'))
+        self.branch_rows = int(os.environ.get('IPAVSR_BRANCH_ROWS', str(1 << 30)))
         deps, self._branch_of = {}, {}
         for l in self.layers:
             ins = [i for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]) if i is not None]
@@ -519,6 +520,7 @@ class Engine(object):
             self._branch_of[l] = roots.index(next(iter(deps[l]))) if len(deps[l]) == 1 else None
         self._n_branches = len(roots)
         self._branch_streams = []
+        self._cur_run = None
         # branch layers whose output (also) feeds the trunk: their gradient arrives from the trunk's stream
         self._trunk_fed = set()
         for l in self.layers:
@@ -588,8 +590,7 @@ class Engine(object):
 
     # ---- branch streams (small batches) ------------------------------------------------------------------------------
     def _use_branches(self, N, T):
-        return (self.branch_mode and self.world is None and self._n_branches >= 2 and self._n_branches <= 8 and
-                N * T <= self.branch_rows)
+        return self.branch_mode and 2 <= self._n_branches <= 8 and N * T <= self.branch_rows
 
     def _branch_enter(self, run, b, sync_from_main):
         """Makes branch b's stream current (and the pinned kernel stream).  The first entry of a run — and any entry with
@@ -1559,6 +1560,7 @@ class Engine(object):
         if not softmax_head and not (isinstance(head, L.DenseLayer) and head.nonlinearity.name != 'softmax'):
             raise ValueError('a squared-error objective needs a non-softmax DenseLayer output')
         run.grads[head] = ([dlogits], True)
+        self._cur_run = run
         self._ar_works, self._ar_hi = [], (ar.flat.numel() if (self.world is not None and self.ar_overlap and
                                                                 getattr(self, '_ar_enabled', True)) else None)
         # number of not-yet-processed consumers of every layer: when it reaches zero the layer's gradient is final and
@@ -1755,6 +1757,7 @@ class Engine(object):
         self._join(run)
         if self._ar_hi is not None:
             self._ar_flush(0, final=True)
+        self._cur_run = None
 
     def _ar_flush(self, lo, final=False):
         """All-reduce the finalised tail [lo, hi) of the gradient arena once it is a bucket's worth (or the walk is over)."""
@@ -1763,6 +1766,16 @@ class Engine(object):
         if final:
             # the side-stream recurrences were joined: everything is ordered before this call on the main stream
             lo = 0
+        run = self._cur_run
+        if run is not None and run.use_branches and not final:
+            # the range was finalised by kernels on several streams (branches, trunk); the collective is ordered behind
+            # the CURRENT stream only, so that stream first waits for the others
+            cur = torch.cuda.current_stream(self.device)
+            for s in [run.main_stream] + [self._branch_streams[b] for b in sorted(run.branches_used)]:
+                if s != cur:
+                    ev = torch.cuda.Event()
+                    ev.record(s)
+                    cur.wait_event(ev)
         self._ar_works.append(torch.distributed.all_reduce(self.arena.grad[lo:self._ar_hi], group=self.world[2],
                                                            async_op=True))
         self._ar_hi = lo
