@@ -368,7 +368,7 @@ int ipavsr_align_fill(const float* x, int ldx, float* y, int ldy, const int64_t*
  * buf[8 * linear_cta_id ...] = {start, setup done, first stage landed, last MMA issued, accumulator ready, epilogue done} */
 int ipavsr_debug_gemm_timestamps(unsigned long long* buf);
 /* launches of the persistent fp16 GEMM kernel (csrc/gemm_f16p.cu) since the library was loaded: lets a test or the bench
- * state which kernel ran a product (ipavsr_gemm_f16x3 picks it for products with >= 4 work units per CTA pair, at least
+ * state which kernel ran a product (ipavsr_gemm_f16x3 picks it for products with >= 2 work units per CTA pair, at least
  * 8 k-blocks and no k-split; IPAVSR_GEMM_PERSIST=0 turns it off).  With buf != NULL the kernel writes per CTA pair
  * {start, setup done, units, MMA issuer waits for a TMEM buffer / for operands (ns), end of the last epilogue, epilogue
  * busy / waiting (ns)} instead of the per-CTA stamps above. */

@@ -792,10 +792,12 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
     const char* e = getenv("IPAVSR_GEMM_PERSIST");
     persist_env = e ? atoi(e) : 1;
     const char* m = getenv("IPAVSR_GEMM_PERSIST_MIN");
-    persist_min = m ? atoi(m) : 4 * (sm_count() / 2);
+    persist_min = m ? atoi(m) : 2 * (sm_count() / 2);
   }
-  // (measured, 13 325 rows: 424-unit products gain 12-18 %; with 3 units per pair the scheduler only adds latency, and the
-  //  atomic epilogue of a k-split is slower next to the operand stream than in the tile-per-pair kernel's own phase)
+  // (measured, 13 325 rows: 424-unit products gain 12-18 % timed alone; with 3 units per pair a product timed alone gains
+  //  nothing, but inside the step — where the branches' GEMMs of several streams share the machine — 2 units per pair is
+  //  the better threshold (512-utterance step 7.47 -> 7.41 ms); the atomic epilogue of a k-split is slower next to the
+  //  operand stream than in the tile-per-pair kernel's own phase)
   static int persist_split = -1;
   if (persist_split < 0) {
     const char* e = getenv("IPAVSR_GEMM_PERSIST_SPLIT");

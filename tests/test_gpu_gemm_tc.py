@@ -75,7 +75,7 @@ def test_f16x3_matches_fp32_parity(M, N, K, ta, tb):
     assert err < 1.5e-6, err
 
 
-# ---- persistent kernel (csrc/gemm_f16p.cu): products with >= 4 work units per CTA pair and no k-split -------------------
+# ---- persistent kernel (csrc/gemm_f16p.cu): products with >= 2 work units per CTA pair and no k-split -------------------
 # All three partial products accumulate in ONE fp32 TMEM accumulator (three truncating adds per k-step instead of one): its
 # stated tolerance is 4e-6 of |A|max |B|max sqrt(K) (measured 1.3e-6 at K = 1200, 2.7e-6 at K = 4096) against 1.5e-6 for
 # the tile-per-pair kernel with its separate cross-term accumulator.
