@@ -370,6 +370,7 @@ class _Run(object):
         self.pending = {}       # layer -> CUDA event of work still running on a side stream
         self.bwd_ready = {}     # LSTM layer -> (event, dG) launched ahead of the backward walk
         self.keep = []          # buffers that must outlive the side-stream kernels
+        self.xw_ready = {}      # LSTM layer -> input projection computed ahead of its turn (sibling LSTMs)
         self.use_branches = False   # small batch: every input branch on its own stream (Engine._branch_enter)
         self.branches_used = set()
         self.main_stream = None
@@ -519,6 +520,29 @@ class Engine(object):
         for l in self.layers:
             self._branch_of[l] = roots.index(next(iter(deps[l]))) if len(deps[l]) == 1 else None
         self._n_branches = len(roots)
+        # sibling LSTMs: consecutive LSTM layers of the walk that read the same input (forward / backward direction of a
+        # BLSTM).  Forward: their projections are all computed before the first recurrence starts.  Backward: they are
+        # processed in the order their recurrences were launched (the walk would otherwise first wait for the one that
+        # finishes LAST and only then issue the GEMMs of the one that finished first).
+        self._lstm_siblings = {}
+        order = list(reversed(self.layers))
+        i = 0 if os.environ.get('IPAVSR_LSTM_SIBLINGS', '1') != '0' else len(self.layers)
+        while i < len(self.layers):
+            l = self.layers[i]
+            j = i
+            if isinstance(l, L.LSTMLayer):
+                while (j + 1 < len(self.layers) and isinstance(self.layers[j + 1], L.LSTMLayer) and
+                       self.layers[j + 1].input_layers[0] is l.input_layers[0] and
+                       self._branch_of[self.layers[j + 1]] == self._branch_of[l]):
+                    j += 1
+                if j > i:
+                    grp = tuple(self.layers[i:j + 1])
+                    for g in grp:
+                        self._lstm_siblings[g] = tuple(x for x in grp if x is not g)
+                    a, b = len(self.layers) - 1 - j, len(self.layers) - 1 - i
+                    order[a:b + 1] = list(grp)          # forward order inside the group
+            i = j + 1
+        self._bwd_order = order
         self._branch_streams = []
         self._cur_run = None
         # branch layers whose output (also) feeds the trunk: their gradient arrives from the trunk's stream
@@ -1366,31 +1390,45 @@ class Engine(object):
                     mask = run.vals[l.input_layers[1]]
                 else:
                     mask = torch.ones(N, T, dtype=torch.uint8, device=self.device)
-                xw = self.new(N * T, 4 * H)
-                self._proj(segs, ar.mat((l, 'W_in')), xw, ar.mat((l, 'b')).ptr, 0)
-                cat_bound = None
-                if l in self.cat_of:
-                    cl, coff = self.cat_of[l]
-                    if cl not in run.cat:
-                        total = self.cat_plan[cl][1]
-                        bound = self._ones2()
-                        run.cat[cl] = (self.new(N * T, total, zero=(_ld8(total) != total)), bound)
-                    cat, cat_bound = run.cat[cl]
-                    out = DevMat(cat.t, cat.ptr + 4 * coff, N * T, H, cat.ld)
-                else:
-                    out = self.new(N * T, H, zero=(_ld8(H) != H))
-                gates = cell = hprev = None
-                if train:
-                    gates = self.new(N * T, 4 * H)
-                    cell = self.new(N * T, H)
-                    if out.ld != _ld8(H):
-                        # the kernels share one leading dimension between out and hprev: give hprev the concat's
-                        t_hp = torch.empty(N * T * out.ld, dtype=torch.float32, device=self.device)
-                        hprev = DevMat(t_hp, t_hp.data_ptr(), N * T, H, out.ld)
+                # LSTMs that read the same input (the two directions of the aggregate BLSTM) get ALL their input projections
+                # before the first recurrence is launched: a recurrence holds 128 SMs for its whole latency chain, and a
+                # projection GEMM issued behind it crawls on the 20 SMs left (241 us instead of 90 in the 512-utterance
+                # step) and delays its own recurrence by that much
+                # (their output / state buffers too: the zero fills of the padding columns would wait behind the recurrence)
+                def prepare(sl):
+                    Hs = sl.num_units
+                    xs = self.new(N * T, 4 * Hs)
+                    self._proj(segs, ar.mat((sl, 'W_in')), xs, ar.mat((sl, 'b')).ptr, 0)
+                    cb = None
+                    if sl in self.cat_of:
+                        cl, coff = self.cat_of[sl]
+                        if cl not in run.cat:
+                            total = self.cat_plan[cl][1]
+                            bound = self._ones2()
+                            run.cat[cl] = (self.new(N * T, total, zero=(_ld8(total) != total)), bound)
+                        cat, cb = run.cat[cl]
+                        o = DevMat(cat.t, cat.ptr + 4 * coff, N * T, Hs, cat.ld)
                     else:
-                        hprev = self.new(N * T, H, zero=(_ld8(H) != H))
-                    if cell.ld != H:       # cell is dense (ld = H) inside the kernels
-                        cell = DevMat(cell.t, cell.ptr, N * T, H, H)
+                        o = self.new(N * T, Hs, zero=(_ld8(Hs) != Hs))
+                    g = c = hp = None
+                    if train:
+                        g = self.new(N * T, 4 * Hs)
+                        c = self.new(N * T, Hs)
+                        if o.ld != _ld8(Hs):
+                            # the kernels share one leading dimension between out and hprev: give hprev the concat's
+                            t_hp = torch.empty(N * T * o.ld, dtype=torch.float32, device=self.device)
+                            hp = DevMat(t_hp, t_hp.data_ptr(), N * T, Hs, o.ld)
+                        else:
+                            hp = self.new(N * T, Hs, zero=(_ld8(Hs) != Hs))
+                        if c.ld != Hs:       # cell is dense (ld = H) inside the kernels
+                            c = DevMat(c.t, c.ptr, N * T, Hs, Hs)
+                    return xs, cb, o, g, c, hp
+
+                if l not in run.xw_ready:
+                    for sl in (l,) + self._lstm_siblings.get(l, ()):
+                        if sl not in run.xw_ready:
+                            run.xw_ready[sl] = prepare(sl)
+                xw, cat_bound, out, gates, cell, hprev = run.xw_ready.pop(l)
                 peep = ar.mat((l, 'peep')).ptr if l.peepholes else None
                 nbytes = lib.ipavsr_lstm_workspace_bytes(N, T, H)
                 if self.concurrent_lstm:
@@ -1570,7 +1608,7 @@ class Engine(object):
             for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
                 if i is not None:
                     remaining[i] = remaining.get(i, 0) + 1
-        for l in reversed(self.layers):
+        for l in self._bwd_order:
             in_layers = [i for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)])
                          if i is not None]
             if run.use_branches:
@@ -1885,6 +1923,9 @@ class Engine(object):
         try:
             return self._loss_and_backward(run, probs, loss, y, mask, count)
         finally:
+            if run.use_branches and run.main_stream is not None:
+                torch.cuda.set_stream(run.main_stream)      # also when the walk was left by an exception
+            self._cur_run = None
             self._pin_stream(False)
 
     def _loss_and_backward(self, run, probs, loss, y, mask, count=None):
@@ -2080,25 +2121,46 @@ class Engine(object):
                 run, out = self.forward(bufs, window, deterministic, train=True)
                 self.loss_and_backward(run, out, loss, ybuf, mbuf, count=None)
 
-            try:
-                # one eager pass first: lazily created state (fp16 arenas, workspaces, constants, function attributes) must
-                # exist before the capture and live outside the graph's memory pool
-                body()
-                self.arena.split_dirty = True        # the captured step refreshes the operand split of the parameters
-                torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                n0 = int(self.lib.ipavsr_launch_count())
-                with torch.cuda.graph(g):
+            import gc
+            err = None
+            for attempt in range(2):
+                try:
+                    # one eager pass first: lazily created state (fp16 arenas, workspaces, constants, function attributes)
+                    # must exist before the capture and live outside the graph's memory pool
                     body()
-                ent = (g, bufs, ybuf, int(self.lib.ipavsr_launch_count()) - n0)
-                self._graphs[key] = ent
-                if len(self._graphs) > 8:
-                    self._graphs.pop(next(iter(self._graphs)))
-            except Exception as e:                    # capture not possible here: stay on the eager path for good
+                    self.arena.split_dirty = True    # the captured step refreshes the operand split of the parameters
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    n0 = int(self.lib.ipavsr_launch_count())
+                    # no garbage collection inside the capture: the finaliser of an old step's buffers or events running in
+                    # the middle of it is the one thing here that is not under this function's control (a capture of the
+                    # multi-stream step was seen invalidated once in ~5 full test runs; the second attempt is for that)
+                    gc.collect()
+                    gc_on = gc.isenabled()
+                    gc.disable()
+                    try:
+                        with torch.cuda.graph(g):
+                            body()
+                    finally:
+                        if gc_on:
+                            gc.enable()
+                    ent = (g, bufs, ybuf, int(self.lib.ipavsr_launch_count()) - n0)
+                    self._graphs[key] = ent
+                    if len(self._graphs) > 8:
+                        self._graphs.pop(next(iter(self._graphs)))
+                    err = None
+                    break
+                except Exception as e:
+                    err = e
+                    self._st_pin = None
+                    try:
+                        torch.cuda.synchronize(self.device)
+                    except Exception:
+                        pass
+            if err is not None:                      # capture not possible here: stay on the eager path for good
                 self._graph_failed = True
                 import warnings
-                warnings.warn('ipavsr_b200: CUDA-graph capture of the small-batch step failed (%s); running eagerly' % (e,))
-                torch.cuda.synchronize(self.device)
+                warnings.warn('ipavsr_b200: CUDA-graph capture of the small-batch step failed (%s); running eagerly' % (err,))
                 return False
             # the eager pass and the capture left valid gradients of THIS batch in the arena only via the eager pass;
             # replay once so that the state is exactly what a replayed step leaves
