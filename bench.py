@@ -415,6 +415,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip rooflines[], configs[] and inference_4stream')
     ap.add_argument('--no-prefetch', action='store_true', help='e2e without the double-buffered input prefetch')
+    ap.add_argument('--prefetch-depth', type=int, default=int(os.environ.get('IPAVSR_BENCH_PREFETCH_DEPTH', '1')),
+                    help='e2e: how many steps ahead the upload of a batch is staged (1 = the next step)')
+    ap.add_argument('--only-e2e', action='store_true', help='experiment aid: print the device-resident and e2e step times only')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -530,19 +533,28 @@ def main():
         return (raw, DiffImages(raw), DctFeatures(raw, IMAGE_SHAPE, DCT_COEFF), y, m, THETA)
     cache = [e2e_args(i) for i in range(NB)]
     jt = [0]
+    depth = max(1, min(args.prefetch_depth, NB - 1))
     if not args.no_prefetch:
-        train.prefetch(*cache[0])
+        for k in range(depth):
+            train.prefetch(*cache[k % NB])
 
     def step_e2e():
         i = jt[0]
         jt[0] += 1
         if not args.no_prefetch:
-            # the next step's upload is staged by this call once its own kernels are enqueued (before it reads the loss
+            # the upload of a later step is staged by this call once its own kernels are enqueued (before it reads the loss
             # back): the upload overlaps this step's compute and the staging work hides behind it
-            train.prefetch(*cache[(i + 1) % NB], defer=True)
+            train.prefetch(*cache[(i + depth) % NB], defer=True)
         return train(*cache[i % NB])
     ms_e2e, _ = timed(step_e2e, args.steps, 3)
     eng._prefetched = []
+    if args.only_e2e:
+        if rank == 0:
+            print(json.dumps({'n_gpus': world, 'prefetch_depth': depth, 'ms_dev': ms_dev, 'ms_e2e': ms_e2e,
+                              'value': args.batch * world / (ms_dev * 1e-3), 'e2e': args.batch * world / (ms_e2e * 1e-3)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     # bytes copied host -> device per step: the valid frames of the raw stream, the targets, and the plan's index tables
     # (pack M+1, valid M, unpack / perm / unperm N*T each, order / inv N each, int32; sorted mask N*T bytes; offsets N+1
     # int64) — counted every step although a plan is re-used while the same lengths come back
