@@ -33,10 +33,12 @@ namespace ipavsr {
 // CG = 2: a CTA pair (cluster (2,1,1), same TPC) computes a 256 x BN tile with one cta_group::2 MMA per k-step: each CTA
 // keeps its own 128 rows of A and HALF of the B tile in shared memory (the tensor core of each SM reads both halves),
 // which cuts the L2->SM operand traffic per flop by a third and the shared-memory reads per MMA by a third.
-// OCC = 2: two CTAs (of different pairs) resident per SM, each with half of the shared memory and of the TMEM columns, so
-// that the epilogue of one tile runs under the mainloop of the other (the 128-wide pair tile of the fp16 mode).
-template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG, int OCC = 1>
-__global__ void __launch_bounds__(TC_THREADS, OCC)
+// (Measured and removed in round 2: two CTAs of 128-wide pair tiles per SM, each with half of the shared memory and of the
+//  TMEM columns, so that one tile's epilogue runs under the other's mainloop — no gain, 0.176 vs 0.175 ms for the fc1
+//  forward: the 128-wide tile's mainloop runs at 78 % of the 256-wide tile's rate.  The persistent kernel of gemm_f16p.cu
+//  overlaps the epilogue instead.)
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, TcParams p) {
   constexpr int BKE = F16 ? 2 * TC_BK : TC_BK;        // elements per stage along K (128 bytes either way)
@@ -48,7 +50,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   static_assert(BNL % MNBOX == 0, "the per-CTA share of the B tile must be whole TMA boxes");
   constexpr int NOPER = (NPROD == 3) ? 2 : 1;         // hi (+ lo) copies of each operand
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
-  constexpr int SMEM_BUDGET = (OCC == 2 ? 100 : 200) * 1024;
+  constexpr int SMEM_BUDGET = 200 * 1024;
   constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES < 8 ? SMEM_BUDGET / STAGE_BYTES : 8;
   static_assert(STAGES >= 2, "need at least a double buffer");
   static_assert(!F16 || NPROD == 3, "the fp16 path is the three-product mode");
@@ -56,7 +58,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // number of accumulations into one accumulator.  In the 3xTF32 mode the tiny cross terms (lo*hi + hi*lo) get their
   // own accumulator and the hi*hi terms are spread round-robin (by k-block) over NMAIN accumulators; the epilogue sums
   // them in registers with round-to-nearest.
-  constexpr int TMEM_COLS = (NPROD == 3) ? 512 / OCC : BN;
+  constexpr int TMEM_COLS = (NPROD == 3) ? 512 : BN;
   constexpr int NMAIN = (NPROD == 3) ? (TMEM_COLS / BN - 1) : 1;
   static_assert(NMAIN >= 1, "main + cross accumulators must fit the TMEM share of this CTA");
 
@@ -636,16 +638,16 @@ uint64_t gemm_tc_workspace_bytes(int mode, int transA, int transB, int M, int N,
   return 2 * (a + b) * sizeof(float) * 2;   // x2 head-room for leading dimensions up to twice the logical width
 }
 
-template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG, int OCC = 1>
+template <int BN, bool A_MN, bool B_MN, int NPROD, bool F16, int CG>
 static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB, const CUtensorMap& mBlo,
                      TcParams p, cudaStream_t st) {
   constexpr int A_BYTES = TC_BM * TC_BK * 4, B_BYTES = (BN / CG) * TC_BK * 4;
   constexpr int NOPER = (NPROD == 3) ? 2 : 1;
   constexpr int STAGE_BYTES = NOPER * (A_BYTES + B_BYTES);
-  constexpr int SMEM_BUDGET = (OCC == 2 ? 100 : 200) * 1024;
+  constexpr int SMEM_BUDGET = 200 * 1024;
   constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES < 8 ? SMEM_BUDGET / STAGE_BYTES : 8;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD, F16, CG, OCC>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, NPROD, F16, CG>;
   IPAVSR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int mtiles = (p.M + TC_BM - 1) / TC_BM;
   dim3 grid((p.N + BN - 1) / BN, mtiles, p.splits);
@@ -671,13 +673,13 @@ static int launch_tc(const CUtensorMap& mA, const CUtensorMap& mAlo, const CUten
   return IPAVSR_OK;
 }
 
-template <int BN, int NPROD, bool F16, int CG, int OCC = 1>
+template <int BN, int NPROD, bool F16, int CG>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
                           const CUtensorMap& mBlo, TcParams p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
-  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
-  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
-  return launch_tc<BN, true, true, NPROD, F16, CG, OCC>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && !b_mn) return launch_tc<BN, false, false, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
+  if (!a_mn && b_mn) return launch_tc<BN, false, true, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
+  if (a_mn && !b_mn) return launch_tc<BN, true, false, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
+  return launch_tc<BN, true, true, NPROD, F16, CG>(mA, mAlo, mB, mBlo, p, st);
 }
 
 int amax_launch(const float* x, int ldx, int rows, int cols, float* amax, cudaStream_t st);   // f16split.cu
@@ -694,13 +696,6 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
   const bool a_mn = transA != 0;     // A stored [K,M]: M contiguous
   const bool b_mn = transB == 0;     // B stored [K,N]: N contiguous
   int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  // IPAVSR_GEMM_OCC: 0 = 256-wide pair tiles, one CTA per SM; 1 = 128-wide pair tiles, one CTA per SM; 2 = 128-wide pair
-  // tiles, two CTAs per SM (one tile's epilogue under the other's mainloop)
-  static int occ_env = -1;
-  if (occ_env < 0) {
-    const char* e = getenv("IPAVSR_GEMM_OCC");
-    occ_env = e ? atoi(e) : 0;
-  }
   const int bke = f16 ? 2 * TC_BK : TC_BK;      // elements per k-block = 128 bytes
   const int mnbox = f16 ? 64 : 32;              // MN-major box: 128 bytes of M/N, bke k-rows
   CUtensorMap mA, mAlo, mB, mBlo;
@@ -734,8 +729,6 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
     cg_env = (e && e[0] == '1') ? 1 : 2;
   }
   int cg = (BN == 256 && M > TC_BM && cg_env == 2) ? 2 : 1;
-  int occ = 1;
-  if (f16 && cg == 2 && occ_env >= 1) { BN = 128; occ = occ_env >= 2 ? 2 : 1; }
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.act = act; p.accumulate = accumulate;
   p.Chi = Chi; p.Clo = Clo; p.expA = expA; p.expB = expB; p.amax = amax;
@@ -804,7 +797,7 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
     persist_split = (e && e[0] == '1') ? 1 : 0;
   }
   // small K: the unit is epilogue-bound and the tile-per-pair kernel's lockstep epilogue does as well (K = 150: 41 vs 51 us)
-  const bool use_p = f16 && BN == 256 && cg == 2 && occ == 1 && persist_env > 0 && tiles / 2 * splits >= persist_min &&
+  const bool use_p = f16 && BN == 256 && cg == 2 && persist_env > 0 && tiles / 2 * splits >= persist_min &&
                      (splits == 1 || persist_split) && num_kb / splits >= 8;
   if (use_p) {
     // halves along K per stage of the persistent kernel: 64 = 3 stages of 64 KB, 32 = 6 stages of 32 KB.  Measured at
@@ -833,8 +826,6 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
            : (x3 ? dispatch_major<BNV, 3, false, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st)          \
                  : dispatch_major<BNV, 1, false, CGV>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st))
   if (BN == 64) { IPAVSR_TC_DISPATCH(64, 1); }
-  else if (BN == 128 && cg == 2 && occ == 2) { rc = dispatch_major<128, 3, true, 2, 2>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st); }
-  else if (BN == 128 && cg == 2) { rc = dispatch_major<128, 3, true, 2, 1>(a_mn, b_mn, mA, mAlo, mB, mBlo, p, st); }
   else if (BN == 128) { IPAVSR_TC_DISPATCH(128, 1); }
   else if (cg == 2) { IPAVSR_TC_DISPATCH(256, 2); }
   else { IPAVSR_TC_DISPATCH(256, 1); }
