@@ -313,7 +313,7 @@ gemm_f16p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tfull_bar[buf], uph);
       tcgen05_fence_after();
       if (dbg != nullptr && threadIdx.x == 128) { const unsigned long long t1 = gtimer(); dbg[7] += t1 - te; te = t1; }
-      const bool fast_ok = vecC && !split;          // warp-uniform
+      const bool fast_ok = vecC;                    // warp-uniform (k-split units: coalesced float4 atomics)
 #pragma unroll 1
       for (int c0 = half * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= p.N) break;                   // warp-uniform
@@ -339,7 +339,7 @@ gemm_f16p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (fast_ok && n0 + c0 + 32 <= p.N) {
           // ---------------- fast path: a full 32-column chunk, coalesced stores through the staging tile ----------------
           if (row < p.M) {
-            if (p.accumulate) {
+            if (p.accumulate && !split) {
               const float* cpo = p.C + (size_t)row * p.ldc + n0 + c0;
 #pragma unroll
               for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -347,7 +347,7 @@ gemm_f16p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 v[j4] += old.x; v[j4 + 1] += old.y; v[j4 + 2] += old.z; v[j4 + 3] += old.w;
               }
             }
-            if (p.bias != nullptr) {
+            if (p.bias != nullptr && (!split || w.z == 0)) {
               if (vecB) {
 #pragma unroll
                 for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -392,8 +392,11 @@ gemm_f16p_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int qq = 0; qq < 8; ++qq) {
               const int rr = 4 * qq + (lane >> 3);
               const float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + ((jj ^ (rr & 7)) << 2));
-              if (rbase + rr < p.M)
-                *reinterpret_cast<float4*>(p.C + (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj) = o;
+              if (rbase + rr < p.M) {
+                float4* dst = reinterpret_cast<float4*>(p.C + (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj);
+                if (split) atomicAdd(dst, o);
+                else *dst = o;
+              }
             }
             if (p.C16hi != nullptr) {
               // fp16 hi/lo split of the chunk under the static scale, from the same staging tile

@@ -270,7 +270,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     const float cs1 = F16 ? ms1 * (F16_LO_INV) : 1.f;
     float tile_max = 0.f;
-    const bool fast_ok = vec && !split && num_kb > 0;      // warp-uniform
+    // (a k-split tile takes the fast path too: its partial sums go out as float4 atomics from the staging tile, 4 rows x
+    //  128 contiguous bytes per instruction instead of 32 rows x 16 bytes)
+    const bool fast_ok = vec && num_kb > 0;                // warp-uniform
 #pragma unroll 1
     for (int c0 = (warp >= 4 ? 0 : 32); c0 < BN; c0 += 64) {
       if (n0 + c0 >= p.N) break;                   // warp-uniform
@@ -323,14 +325,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float* stg = reinterpret_cast<float*>(smem) + warp * 1024;
           if (row < p.M) {
             float* cpo = p.C + (size_t)row * p.ldc + n0 + c0;
-            if (p.accumulate) {
+            if (p.accumulate && !split) {
 #pragma unroll
               for (int j4 = 0; j4 < 32; j4 += 4) {
                 const float4 old = *reinterpret_cast<const float4*>(cpo + j4);
                 v[j4] += old.x; v[j4 + 1] += old.y; v[j4 + 2] += old.z; v[j4 + 3] += old.w;
               }
             }
-            if (p.bias != nullptr) {
+            if (p.bias != nullptr && (!split || blockIdx.z == 0)) {
 #pragma unroll
               for (int j4 = 0; j4 < 32; j4 += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + j4]);
@@ -364,8 +366,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int qq = 0; qq < 8; ++qq) {
               const int rr = 4 * qq + (lane >> 3);
               const float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + ((jj ^ (rr & 7)) << 2));
-              if (rbase + rr < p.M)
-                *reinterpret_cast<float4*>(p.C + (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj) = o;
+              if (rbase + rr < p.M) {
+                float4* dst = reinterpret_cast<float4*>(p.C + (size_t)(rbase + rr) * p.ldc + n0 + c0 + 4 * jj);
+                if (split) atomicAdd(dst, o);
+                else *dst = o;
+              }
             }
             if (p.C16hi != nullptr) {
               // fp16 hi/lo split of the chunk under the static scale, from the same staging tile: 8 lanes cover 64
@@ -789,8 +794,12 @@ static int gemm_tc_core(int kind, int transA, int transB, int M, int N, int K, c
   }
   // (measured, 13 325 rows: 424-unit products gain 12-18 % timed alone; with 3 units per pair a product timed alone gains
   //  nothing, but inside the step — where the branches' GEMMs of several streams share the machine — 2 units per pair is
-  //  the better threshold (512-utterance step 7.47 -> 7.41 ms); the atomic epilogue of a k-split is slower next to the
-  //  operand stream than in the tile-per-pair kernel's own phase)
+  //  the better threshold (512-utterance step 7.47 -> 7.41 ms); k-split products can go to it as well
+  //  (IPAVSR_GEMM_PERSIST_SPLIT=1): with their partial tiles leaving as coalesced float4 atomics from the staging tile the
+  //  fc1 weight gradient takes 0.153 ms against 0.182 for the tile-per-pair kernel timed alone (with one float4 per row and
+  //  lane the atomic epilogue took 21.8 us per unit, longer than the mainloop it hides under: 0.218 ms) — but inside the
+  //  step, where the weight gradients overlap the other branches' kernels, it changes nothing (7.58 / 7.60 vs 7.62 / 7.55
+  //  ms), so they stay on the kernel with the separate cross-term accumulator and its tighter error bound)
   static int persist_split = -1;
   if (persist_split < 0) {
     const char* e = getenv("IPAVSR_GEMM_PERSIST_SPLIT");
