@@ -506,52 +506,16 @@ class Engine(object):
         # gaps between dependent kernels and the SMs a recurrence kernel leaves free (8.2 -> 7.5 ms).
         self.branch_mode = os.environ.get('IPAVSR_BRANCH_STREAMS', '1') != '0'
         self.branch_rows = int(os.environ.get('IPAVSR_BRANCH_ROWS', str(1 << 30)))
-        deps, self._branch_of = {}, {}
-        for l in self.layers:
-            ins = [i for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]) if i is not None]
-            if isinstance(l, L.InputLayer):
-                deps[l] = frozenset() if l in self.mask_layers else frozenset([l])
-            else:
-                d = frozenset()
-                for i in ins:
-                    d = d | deps.get(i, frozenset())
-                deps[l] = d
-        roots = sorted({next(iter(d)) for d in deps.values() if len(d) == 1}, key=self.layers.index)
-        for l in self.layers:
-            self._branch_of[l] = roots.index(next(iter(deps[l]))) if len(deps[l]) == 1 else None
-        self._n_branches = len(roots)
+        from . import schedule
+        self._branch_of, self._n_branches, self._trunk_fed = schedule.branch_assignment(self.layers, self.mask_layers)
         # sibling LSTMs: consecutive LSTM layers of the walk that read the same input (forward / backward direction of a
         # BLSTM).  Forward: their projections are all computed before the first recurrence starts.  Backward: they are
         # processed in the order their recurrences were launched (the walk would otherwise first wait for the one that
         # finishes LAST and only then issue the GEMMs of the one that finished first).
-        self._lstm_siblings = {}
-        order = list(reversed(self.layers))
-        i = 0 if os.environ.get('IPAVSR_LSTM_SIBLINGS', '1') != '0' else len(self.layers)
-        while i < len(self.layers):
-            l = self.layers[i]
-            j = i
-            if isinstance(l, L.LSTMLayer):
-                while (j + 1 < len(self.layers) and isinstance(self.layers[j + 1], L.LSTMLayer) and
-                       self.layers[j + 1].input_layers[0] is l.input_layers[0] and
-                       self._branch_of[self.layers[j + 1]] == self._branch_of[l]):
-                    j += 1
-                if j > i:
-                    grp = tuple(self.layers[i:j + 1])
-                    for g in grp:
-                        self._lstm_siblings[g] = tuple(x for x in grp if x is not g)
-                    a, b = len(self.layers) - 1 - j, len(self.layers) - 1 - i
-                    order[a:b + 1] = list(grp)          # forward order inside the group
-            i = j + 1
-        self._bwd_order = order
+        self._lstm_siblings, self._bwd_order = schedule.lstm_sibling_groups(
+            self.layers, self._branch_of, os.environ.get('IPAVSR_LSTM_SIBLINGS', '1') != '0')
         self._branch_streams = []
         self._cur_run = None
-        # branch layers whose output (also) feeds the trunk: their gradient arrives from the trunk's stream
-        self._trunk_fed = set()
-        for l in self.layers:
-            if self._branch_of[l] is None:
-                for i in (getattr(l, 'input_layers', None) or [getattr(l, 'input_layer', None)]):
-                    if i is not None and self._branch_of.get(i) is not None:
-                        self._trunk_fed.add(i)
         # CUDA graphs for launch-bound small batches: 'auto' (default) | 'off'  (IPAVSR_GRAPH=0)
         self.graph_mode = 'off' if os.environ.get('IPAVSR_GRAPH', '1') == '0' else 'auto'
         self._graphs, self._graph_failed = {}, False
