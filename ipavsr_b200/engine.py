@@ -516,6 +516,14 @@ class Engine(object):
             self.layers, self._branch_of, os.environ.get('IPAVSR_LSTM_SIBLINGS', '1') != '0')
         self._branch_streams = []
         self._cur_run = None
+        # The loss is final long before the step is: right after the loss kernel (single process) or after the first
+        # gradient bucket's all-reduce, which carries the arena's tail (data parallel).  It is copied to pinned host memory
+        # at that point on a stream of its own, and the compiled function returns as soon as THAT copy has landed — with the
+        # backward pass and the update still running.  The caller's next call then enqueues behind them, so the device
+        # never waits for the host between steps (IPAVSR_EARLY_LOSS=0: read the loss after the update, as before).
+        self.early_loss = os.environ.get('IPAVSR_EARLY_LOSS', '1') != '0'
+        self._early_loss_ok = False          # set per call by function(...): no L2 term, not a graph replay
+        self._loss_stream = self._loss_host = self._loss_ready = None
         # CUDA graphs for launch-bound small batches: 'auto' (default) | 'off'  (IPAVSR_GRAPH=0)
         self.graph_mode = 'off' if os.environ.get('IPAVSR_GRAPH', '1') == '0' else 'auto'
         self._graphs, self._graph_failed = {}, False
@@ -1778,8 +1786,11 @@ class Engine(object):
                     ev = torch.cuda.Event()
                     ev.record(s)
                     cur.wait_event(ev)
+        first = self._ar_hi == self.arena.flat.numel()       # the bucket that carries the arena's tail: the loss sums
         self._ar_works.append(torch.distributed.all_reduce(self.arena.grad[lo:self._ar_hi], group=self.world[2],
                                                            async_op=True))
+        if first and not final:
+            self._loss_early_copy(self._ar_works[-1])
         self._ar_hi = lo
 
     def _release(self, run, ins, remaining):
@@ -1895,6 +1906,7 @@ class Engine(object):
     def _loss_and_backward(self, run, probs, loss, y, mask, count=None):
         st, ar = self.stream, self.arena
         plan = run.plan
+        self._loss_ready = None
         # a packed / length-sorted run computes the loss in its own utterance order: targets follow, the mask is the plan's
         p = run.out_sorted[0] if plan is not None else probs[0]
         tail = ar.grad.data_ptr() + 4 * ar.tail
@@ -1945,10 +1957,14 @@ class Engine(object):
             ar.grad[ar.tail + 1: ar.tail + 2].fill_(float(n_glob))
             _lib.call('ipavsr_squared_error', p.ptr, p.ld, td.ptr, td.ld, tail, dlogits.ptr, dlogits.ld, p.rows, p.cols,
                       1.0 / n_glob, st)
+            if self.world is None:
+                self._loss_early_copy()
             self.backward(run, dlogits, softmax_head=False)
             return
         else:
             raise ValueError('unknown loss %r' % (loss,))
+        if self.world is None:
+            self._loss_early_copy()
         self.backward(run, dlogits)
 
     def _target_matrix(self, y, p):
@@ -2146,9 +2162,41 @@ class Engine(object):
         else:
             torch.distributed.all_reduce(self.arena.grad, group=self.world[2])
 
+    def _loss_early_copy(self, work=None):
+        """[loss sum, normaliser, rank count] -> pinned host memory, ordered behind the current stream (and behind the NCCL
+        work that summed them over the ranks); read_loss() then waits for this copy only."""
+        if not (self.early_loss and self._early_loss_ok) or torch.cuda.is_current_stream_capturing():
+            return
+        ar = self.arena
+        if self._loss_stream is None:
+            self._loss_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._loss_host = torch.empty(4, dtype=torch.float32).pin_memory()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        ls = self._loss_stream
+        ls.wait_event(ev)
+        with torch.cuda.stream(ls):
+            if work is not None:
+                work.wait()
+            if os.environ.get('IPAVSR_EARLY_LOSS_DMA', '0') == '1':
+                self._loss_host.copy_(ar.grad[ar.tail: ar.tail + 4], non_blocking=True)
+            else:
+                # written by a kernel straight into the (device-mapped) pinned buffer: a D2H copy would queue on a copy
+                # engine behind the bulk upload of the next batch
+                _lib.call('ipavsr_copy2d', ar.grad.data_ptr() + 4 * ar.tail, 4, self._loss_host.data_ptr(), 4, 1, 4, None, 0,
+                          C.c_void_p(ls.cuda_stream))
+            done = torch.cuda.Event()
+            done.record(ls)
+        self._loss_ready = done
+
     def read_loss(self):
         ar = self.arena
-        h = ar.grad[ar.tail: ar.tail + 3].cpu().numpy()
+        ev, self._loss_ready = self._loss_ready, None
+        if ev is not None:
+            ev.synchronize()
+            h = self._loss_host.numpy()[:3].copy()
+        else:
+            h = ar.grad[ar.tail: ar.tail + 3].cpu().numpy()
         w = h[2] if h[2] > 0 else 1.0      # the (already global) count was summed world_size times
         return np.float32(h[0] / (h[1] / w))
 

@@ -180,6 +180,12 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
             return eng.loss_only(out, loss_name, y, mask, l2=l2)
         graphed = False
+        # early loss read-back (Engine._loss_early_copy): not with an L2 term (added to the loss after the backward pass), and
+        # only for device-resident inputs — with host inputs the early return moves the NEXT batch's upload under this step's
+        # forward pass, and the end-to-end step got slower and erratic (7.46 -> 7.6 .. 8.1 ms), so those calls keep reading
+        # the loss after the update
+        eng._early_loss_ok = (not l2 and not pending and
+                              all(hasattr(a, 'is_cuda') and a.is_cuda for a in feed.values()))
         if not dropout_masks and eng.graph_eligible(feed, y, pred.deterministic, l2):
             with _Nvtx('forward + loss + backward (CUDA graph)'):
                 graphed = eng.graph_step(feed, window, y, mask_layer, loss_name, pred.deterministic)
