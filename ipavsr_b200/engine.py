@@ -514,6 +514,18 @@ class Engine(object):
         # finishes LAST and only then issue the GEMMs of the one that finished first).
         self._lstm_siblings, self._bwd_order = schedule.lstm_sibling_groups(
             self.layers, self._branch_of, os.environ.get('IPAVSR_LSTM_SIBLINGS', '1') != '0')
+        # data parallel: a bucket [lo, hi) of the gradient arena goes out once every layer at or behind lo has been walked.
+        # Siblings are walked in forward order, i.e. the one with the LOWER arena offset first: the group's range is
+        # released by its last member only
+        self._flush_lo = dict(self._layer_lo)
+        for l, others in self._lstm_siblings.items():
+            grp = sorted((l,) + tuple(others), key=self.layers.index)
+            if l is grp[-1]:
+                los = [self._layer_lo[g] for g in grp if g in self._layer_lo]
+                if los:
+                    self._flush_lo[l] = min(los)
+            else:
+                self._flush_lo.pop(l, None)
         self._branch_streams = []
         self._cur_run = None
         # The loss is final long before the step is: right after the loss kernel (single process) or after the first
@@ -1758,8 +1770,8 @@ class Engine(object):
             else:
                 del run.grads[l]
             self._release(run, in_layers, remaining)
-            if self._ar_hi is not None and l in self._layer_lo:
-                self._ar_flush(self._layer_lo[l])
+            if self._ar_hi is not None and l in self._flush_lo:
+                self._ar_flush(self._flush_lo[l])
         if run.use_branches:
             self._branch_leave(run)
             for b in sorted(run.branches_used):

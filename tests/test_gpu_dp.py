@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _train(name, rank, world, steps, q=None, port=None):
+def _train(name, rank, world, steps, q=None, port=None, dev_inputs=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     import model_util as MU
@@ -48,10 +48,15 @@ def _train(name, rank, world, steps, q=None, port=None):
         parallel.attach(train.engine)
     lo, hi = parallel.shard_bounds(N, rank, world)
     losses = []
+    # dev_inputs: everything resident in HBM — the call then returns as soon as the loss has been read back, which under
+    # data parallelism is after the first gradient bucket's all-reduce (Engine._loss_early_copy)
+    up = (lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()) if dev_inputs else (lambda a: a)
     for _ in range(steps):
         # device tensors for the mask so that the count is taken (and all-reduced) on the device
-        losses.append(float(train(xs[0][lo:hi], y[lo:hi], torch.from_numpy(mask[lo:hi]).cuda(),
-                                  *[x[lo:hi] for x in xs[1:]], 3)))
+        losses.append(float(train(up(xs[0][lo:hi]), up(y[lo:hi]), torch.from_numpy(mask[lo:hi]).cuda(),
+                                  *[up(x[lo:hi]) for x in xs[1:]], 3)))
+    if dev_inputs and world > 1:
+        assert train.engine.early_loss and train.engine._early_loss_ok
     vals = [p.get_value() for p in params]
     if q is not None:
         if rank == 0:
@@ -64,15 +69,16 @@ def _train(name, rank, world, steps, q=None, port=None):
 
 def _worker(rank, world, port, name, q, bucket):
     torch.cuda.set_device(rank)
-    # a tiny bucket makes the overlapped all-reduce go out in many pieces during the backward walk; 0 = one all-reduce after it
+    # a tiny bucket makes the overlapped all-reduce go out in many pieces during the backward walk; 0 = one all-reduce after
+    # it; a negative bucket = the tiny bucket with device-resident inputs (early loss read-back)
     if bucket:
-        os.environ['IPAVSR_AR_BUCKET'] = str(bucket)
+        os.environ['IPAVSR_AR_BUCKET'] = str(abs(bucket))
     else:
         os.environ['IPAVSR_AR_OVERLAP'] = '0'
-    _train(name, rank, world, 3, q, port)
+    _train(name, rank, world, 3, q, port, dev_inputs=bucket < 0)
 
 
-@pytest.mark.parametrize('bucket', [512, 0])
+@pytest.mark.parametrize('bucket', [512, 0, -512])
 @pytest.mark.parametrize('name', ['adenet_v2', 'adenet_v1'])
 def test_two_gpu_training_matches_single_gpu(name, bucket):
     if torch.cuda.device_count() < 2:
@@ -81,7 +87,7 @@ def test_two_gpu_training_matches_single_gpu(name, bucket):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     import zlib
-    port = 29900 + (zlib.crc32(name.encode()) % 40) * 2 + (1 if bucket else 0)
+    port = 29900 + (zlib.crc32(name.encode()) % 40) * 3 + (0 if not bucket else (1 if bucket > 0 else 2))
     procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q, bucket)) for r in range(2)]
     for p in procs:
         p.start()
