@@ -11,6 +11,8 @@ callable with the same positional arguments that runs the B200 engine.
 `tensor` provides the placeholder constructors the runners use (`T.tensor3`, `T.matrix`, `T.imatrix`,
 `T.ivector`, `T.iscalar`).
 """
+import os
+
 import numpy as np
 
 from . import layers as L
@@ -89,6 +91,9 @@ class shared(object):
 
     def set_value(self, v):
         self.value = np.float32(v)
+
+
+_EARLY_HOST = os.environ.get('IPAVSR_EARLY_LOSS_HOST', '0') == '1'     # experiment: early return for host inputs too
 
 
 def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_unused_input='raise', **engine_kw):
@@ -184,8 +189,8 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         # only for device-resident inputs — with host inputs the early return moves the NEXT batch's upload under this step's
         # forward pass, and the end-to-end step got slower and erratic (7.46 -> 7.6 .. 8.1 ms), so those calls keep reading
         # the loss after the update
-        eng._early_loss_ok = (not l2 and not pending and
-                              all(hasattr(a, 'is_cuda') and a.is_cuda for a in feed.values()))
+        eng._early_loss_ok = (not l2 and (_EARLY_HOST or (not pending and all(hasattr(a, 'is_cuda') and a.is_cuda
+                                                                              for a in feed.values()))))
         if not dropout_masks and eng.graph_eligible(feed, y, pred.deterministic, l2):
             with _Nvtx('forward + loss + backward (CUDA graph)'):
                 graphed = eng.graph_step(feed, window, y, mask_layer, loss_name, pred.deterministic)

@@ -35,6 +35,7 @@ for b in range(NB):
 
 def run(step, n=24, warm=4):
     host_ms, wall = [], []
+    torch.cuda.synchronize()
     for i in range(n + warm):
         t0 = time.perf_counter()
         step(i)
@@ -42,6 +43,8 @@ def run(step, n=24, warm=4):
         if i >= warm:
             host_ms.append((marks[-1] - t0) * 1e3)
             wall.append((t1 - t0) * 1e3)
+    torch.cuda.synchronize()
+    print('   per-call wall (ms):', ' '.join('%.1f' % w for w in wall))
     return np.median(host_ms), np.median(wall)
 
 h, w = run(lambda i: train(dev[i % NB][0][0], dev[i % NB][0][1], dev[i % NB][0][2], dev[i % NB][2], dev[i % NB][1], bench.THETA))
