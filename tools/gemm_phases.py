@@ -1,6 +1,8 @@
 """Per-CTA phase timing of the tensor-core GEMM (globaltimer stamps written by the kernel when enabled).
     python tools/gemm_phases.py [f16|tf32x3] [ta tb M N K]"""
 import ctypes as C, os, sys
+os.environ.setdefault('IPAVSR_GEMM_PERSIST', '0')     # this tool reads the tile-per-pair kernel's stamps; the persistent
+                                                      # kernel (gemm_f16p.cu) has its own accounting: tools/gemm_phases_p.py
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
