@@ -54,10 +54,16 @@ train.prefetch(*args[0])
 def e2e(i):
     train.prefetch(*args[(i + 1) % NB], defer=True)
     train(*args[i % NB])
+ms0 = torch.cuda.memory_stats()
 h, w = run(e2e)
+ms1 = torch.cuda.memory_stats()
+print('   cudaMalloc calls during the loop: %d, cudaFree: %d, reserved %.0f -> %.0f MB' % (
+    ms1.get('num_device_alloc', 0) - ms0.get('num_device_alloc', 0), ms1.get('num_device_free', 0) - ms0.get('num_device_free', 0),
+    ms0['reserved_bytes.all.current'] / 2**20, ms1['reserved_bytes.all.current'] / 2**20))
 print('batch %d end to end:      host %.2f ms of a %.2f ms step' % (B, h, w))
-import cProfile, pstats
-pr = cProfile.Profile(); pr.enable()
-for i in range(12): e2e(i)
-pr.disable()
-pstats.Stats(pr).sort_stats('cumulative').print_stats(32)
+if os.environ.get('HOST_TIME_PROFILE') == '1':
+    import cProfile, pstats
+    pr = cProfile.Profile(); pr.enable()
+    for i in range(12): e2e(i)
+    pr.disable()
+    pstats.Stats(pr).sort_stats('cumulative').print_stats(32)
