@@ -93,9 +93,6 @@ class shared(object):
         self.value = np.float32(v)
 
 
-_EARLY_HOST = os.environ.get('IPAVSR_EARLY_LOSS_HOST', '0') == '1'     # experiment: early return for host inputs too
-
-
 def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_unused_input='raise', **engine_kw):
     if isinstance(outputs, (list, tuple)):
         if len(outputs) != 1:
@@ -185,13 +182,20 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
             run, out = eng.forward(feed, window, pred.deterministic, train=False, dropout_masks=dropout_masks)
             return eng.loss_only(out, loss_name, y, mask, l2=l2)
         graphed = False
-        # early loss read-back (Engine._loss_early_copy): not with an L2 term (added to the loss after the backward pass), and
-        # only for device-resident inputs — with host inputs the early return moves the NEXT batch's upload under this step's
-        # forward pass, and the end-to-end step got slower and erratic (7.46 -> 7.6 .. 8.1 ms), so those calls keep reading
-        # the loss after the update
-        eng._early_loss_ok = (not l2 and (_EARLY_HOST or (not pending and all(hasattr(a, 'is_cuda') and a.is_cuda
-                                                                              for a in feed.values()))))
-        if not dropout_masks and eng.graph_eligible(feed, y, pred.deterministic, l2):
+        graph_ok = not dropout_masks and eng.graph_eligible(feed, y, pred.deterministic, l2)
+        # Early loss read-back (Engine._loss_early_copy): not with an L2 term (added to the loss after the backward pass) and
+        # not for a graph replay.  A deferred prefetch is then staged FIRST: this call returns as soon as its loss is final,
+        # the host has ~3 ms of slack per step, and an upload issued before the step's kernels is the one order in which the
+        # end-to-end step stays at the device-resident time (7.08 ms; staged after them it settles at 8.0 ms, and with the
+        # late read an up-front staging delays the enqueue: 8.6 ms — tools/host_time.py)
+        # (Not when the deferred upload is large — three padded host streams, 204 MB, are link-bound for longer than a step:
+        # staged first they cost 10.0 ms per step, staged last with the early return 7.8 .. 9.6 ms erratically, staged last
+        # with the late read a steady 8.7 ms, which is what such calls keep.)
+        big = _pending_bytes() > (128 << 20)
+        eng._early_loss_ok = not l2 and not graph_ok and not big
+        if eng._early_loss_ok and eng.early_loss:
+            _run_deferred()
+        if graph_ok:
             with _Nvtx('forward + loss + backward (CUDA graph)'):
                 graphed = eng.graph_step(feed, window, y, mask_layer, loss_name, pred.deterministic)
         if not graphed:
@@ -215,6 +219,17 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
         return eng.read_loss()
 
     pending = []
+
+    def _pending_bytes():
+        """Host bytes the deferred prefetches will upload (device tensors and derived streams cost nothing)."""
+        n = 0
+        for feed in pending:
+            for a in feed.values():
+                if hasattr(a, 'is_cuda'):
+                    n += 0 if a.is_cuda else a.numel() * a.element_size()
+                elif hasattr(a, 'nbytes'):
+                    n += int(a.nbytes)
+        return n
 
     def _run_deferred():
         while pending:

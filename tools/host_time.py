@@ -51,8 +51,9 @@ h, w = run(lambda i: train(dev[i % NB][0][0], dev[i % NB][0][1], dev[i % NB][0][
 print('batch %d device-resident: host %.2f ms of a %.2f ms step' % (B, h, w))
 args = [(r, DiffImages(r), DctFeatures(r, bench.IMAGE_SHAPE, bench.DCT_COEFF), y, m, bench.THETA) for (r, m, y) in host]
 train.prefetch(*args[0])
+DEFER = os.environ.get('HOST_TIME_DEFER', '1') == '1'     # 0: the next batch is staged BEFORE this call enqueues its kernels
 def e2e(i):
-    train.prefetch(*args[(i + 1) % NB], defer=True)
+    train.prefetch(*args[(i + 1) % NB], defer=DEFER)
     train(*args[i % NB])
 ms0 = torch.cuda.memory_stats()
 h, w = run(e2e)
