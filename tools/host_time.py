@@ -1,6 +1,7 @@
 """Host time per training step: from the call of the compiled function to the point where it blocks on the loss
 (everything the host has to do to keep the device fed), device-resident inputs vs the end-to-end path (pinned host raw
-stream, derived streams, deferred prefetch).   python tools/host_time.py [batch]"""
+stream, derived streams, deferred prefetch), with per-call wall times and the allocator's cudaMalloc count.
+    python tools/host_time.py [batch]        IPAVSR_EARLY_LOSS=0: late loss read;  HOST_TIME_DEFER=0: prefetch(..., defer=False)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
