@@ -238,8 +238,9 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
     def prefetch(*args, **kw):
         """Stage the host inputs of a LATER call (same positional arguments as the call itself) on the engine's copy stream:
         the copy overlaps whatever the device is doing, and the matching call picks the staged buffers up instead of
-        copying again.  `defer=True` postpones the staging to the next call of this function, which performs it after it
-        has enqueued its own kernels and before it blocks on its result — the recommended double-buffered loop:
+        copying again.  `defer=True` postpones the staging to the next call of this function, which performs it where it
+        costs the step nothing (before its own kernels when the call returns early on its loss — the usual case —, behind
+        them when it reads the loss after the update) — the recommended double-buffered loop:
 
             train.prefetch(*batch[0])
             for i in range(n):
@@ -252,9 +253,8 @@ def function(inputs, outputs=None, updates=None, allow_input_downcast=True, on_u
             raise TypeError('expected %d arguments, got %d' % (len(slots), len(args)))
         feed = {layer: a for (kind, layer), a in zip(slots, args) if kind == 'input'}
         if kw.get('defer'):
-            # staged by the NEXT call of this function, after it has enqueued its own kernels and before it waits for its
-            # result: the host work of staging hides behind the device's compute, and an upload issued behind the
-            # compute kernels does not hold them up (csrc/pack.cu)
+            # staged by the NEXT call of this function (see fn: first thing with the early loss read-back, otherwise after it
+            # has enqueued its own kernels and before it waits for its result)
             pending.append(feed)
         else:
             eng.prefetch(feed)
