@@ -7,12 +7,17 @@ backward.  Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--
 PARITY STATUS: *partially pinned*.
   * `oracle/preprocessing.py` (a10–a14) is pinned against outputs of the reference's own
     `utils/preprocessing.py` executed in the build container (`tests/golden/make_golden.py`).
-  * The Theano/Lasagne arithmetic below (Dense, DeltaLayer, LSTMLayer, BatchNorm, losses, updates) is
-    **parity unpinned**: Theano, Lasagne and nolearn are not in `/root/reference`, are pinned by the reference
-    only as "master" (`README.md:30-33`), are not installable here, and the reference ships no golden vectors
-    for them.  These functions restate the reference's own code where it exists
-    (`utils/signal.py:7-80`, `custom/objectives.py:27-37`, `custom/updates.py:73-99`,
-    `custom/layers.py:178-228`) and the published Lasagne semantics elsewhere; they are
+  * The parts of the Theano-level arithmetic that live in the REFERENCE's own sources — the DeltaLayer
+    (`utils/signal.py:7-80`, a2), `temporal_softmax_loss` (`custom/objectives.py:27-37`, a8) and `adam_vlr` /
+    `generate_lr_map` (`custom/updates.py:10-99`, a9) — are pinned against vectors made by executing those source files,
+    unmodified, with a NumPy stand-in for the few Theano / Lasagne calls they make
+    (`tests/golden/make_theano_shim_golden.py` -> `tests/golden/theano_shim.npz`, checked in
+    `tests/test_oracle_shim_golden.py`: `delta_fwd` bit for bit).  That is the reference's code run statement by statement,
+    not its compiled Theano graph.
+  * What lives inside Lasagne / nolearn (Dense, LSTMLayer, BatchNorm, Dropout, the other update rules and objectives;
+    rows a1, a3–a7, f4) is **parity unpinned**: Theano, Lasagne and nolearn are not in `/root/reference`, are pinned by the
+    reference only as "master" (`README.md:30-33`), are not installable here, and the reference ships no golden vectors
+    for them.  These functions restate the published Lasagne semantics; they are
     cross-checked against an independent torch-float64 autograd restatement and finite differences in
     `tests/test_oracle_*.py`, and against the hand-derived vectors of SURVEY Appendix C.
 
