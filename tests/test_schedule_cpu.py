@@ -79,3 +79,58 @@ def test_sibling_lstms_and_backward_order(name, fusion):
     # switched off: plain reversed order, no groups
     sib0, order0 = schedule.lstm_sibling_groups(layers, branch_of, enabled=False)
     assert not sib0 and order0 == list(reversed(layers))
+
+
+def test_random_layer_graphs_keep_the_invariants():
+    """Random multi-stream graphs (hypothesis): a layer is a branch layer iff it depends on exactly one non-mask input; the
+    backward order is a reverse topological order of the whole graph; siblings read the same input and never each other."""
+    from hypothesis import given, settings, strategies as hs
+
+    @settings(max_examples=40, deadline=None)
+    @given(hs.integers(1, 4), hs.lists(hs.integers(0, 3), min_size=1, max_size=4), hs.booleans(), hs.integers(0, 2 ** 16))
+    def run(n_streams, depths, blstm, seed):
+        rng = np.random.default_rng(seed)
+        mask = L.InputLayer((None, None), name='mask')
+        tails = []
+        for s in range(n_streams):
+            l = L.InputLayer((None, None, 6 + s), name='in%d' % s)
+            for d in range(depths[s % len(depths)]):
+                l = L.DenseLayer(L.ReshapeLayer(l, (-1, l.output_shape[-1])), 5, name='fc%d_%d' % (s, d))
+                l = L.ReshapeLayer(l, (-1, 7, 5))
+            if rng.integers(0, 2):
+                l = L.DeltaLayer(l, 2, name='delta%d' % s)
+            tails.append(L.LSTMLayer(l, 4, mask_input=mask, name='lstm%d' % s))
+        agg = tails[0] if len(tails) == 1 else (L.ConcatLayer(tails, axis=2) if rng.integers(0, 2) else L.ElemwiseSumLayer(tails))
+        if blstm:
+            f = L.LSTMLayer(agg, 3, mask_input=mask, name='f')
+            b = L.LSTMLayer(agg, 3, mask_input=mask, backwards=True, name='b')
+            agg = L.ElemwiseSumLayer([f, b])
+        out = L.DenseLayer(L.ReshapeLayer(agg, (-1, agg.output_shape[-1])), 3, name='out')
+        layers = L.get_all_layers(out)
+        branch_of, n, trunk_fed = schedule.branch_assignment(layers, {mask})
+        assert n == n_streams
+        # dependency sets, recomputed independently by a graph walk from every layer
+        def deps(l, seen=None):
+            seen = set() if seen is None else seen
+            if isinstance(l, L.InputLayer):
+                return set() if l is mask else {l}
+            r = set()
+            for i in _ins(l):
+                r |= deps(i)
+            return r
+        for l in layers:
+            d = deps(l)
+            assert (branch_of[l] is not None) == (len(d) == 1), l.name
+        sib, order = schedule.lstm_sibling_groups(layers, branch_of)
+        pos = {id(l): k for k, l in enumerate(order)}
+        assert len(pos) == len(layers)
+        for l in layers:
+            for i in _ins(l):
+                assert pos[id(l)] < pos[id(i)]
+        for l, others in sib.items():
+            for o in others:
+                assert o.input_layers[0] is l.input_layers[0] and l not in _ins(o) and o not in _ins(l)
+        if blstm:
+            assert sib.get(f) == (b,) and pos[id(f)] < pos[id(b)]
+
+    run()
